@@ -1,0 +1,414 @@
+"""Static contraction plans: the POD hand-off between the Python planner and the CUDA engine.
+
+A plan is ONE int32 word pool (layout below, mirrored in include/pgx.h) plus ONE packed table blob of
+batch-invariant values (CPTs / clique potentials, reference layout: C-order, first variable slowest,
+pgmpy/factors/discrete/DiscreteFactor.py:91-127).
+
+Every step is the same operation, a fused product + sum-out over a batch of evidence sets b:
+
+    out[o, b] = REDUCE_s  PROD_k  operand_k[ idx_k(o, s) + evoff_k(b) , b ]   ( / divisor_j[idx_j(o), b] )
+
+  * `o` runs over the output scope (row-major over `out dims`), `s` over the summed-out scope;
+  * idx_k is a mixed-radix dot product with per-operand strides (stride 0 = variable not in scope):
+    this replaces the reference's `einsum` product (DiscreteFactor.py:769-777) + `einsum` sum-out
+    (:400-408) without materialising the joint table;
+  * evoff_k(b) = sum_j ev_states[b, slot_j] * stride_j is the evidence reduce (:599-614) folded into
+    operand addressing (the observed axes never appear in any step's scope);
+  * divisors implement DiscreteFactor.divide (:838-863; 0/0 -> 0, x/0 -> inf) after the reduction;
+  * work tables (batch dependent) live in the workspace as [entry][b] (b fastest), const tables in
+    the blob; the last steps' outputs are copied/normalised into out[b, :] by segments
+    (normalise = DiscreteFactor.normalize, :530).
+
+Word pool layout (int32 words; 64-bit values as lo,hi):
+  header[16]: 0 magic 'PGX1' | 1 version | 2 n_ev | 3 n_steps | 4 n_segs | 5 out_elems | 6,7 ws_entries
+              | 8,9 const_entries | 10 step_index_off | 11 segs_off | 12 max_ops | 13 max_axes | 14,15 0
+  step_index[n_steps]: word offset of each step record
+  step record: 0 A (#out axes) | 1 S (#sum axes) | 2 K (#operands) | 3 flags (bit0 max-reduce, bit1 has divisor)
+               | 4,5 out_size | 6,7 sum_size | 8,9 out work offset | 10 level | 11 0
+               | out dims[A] | sum dims[S] | K operand records | evidence pairs
+  operand record (6+A+S words): 0 kind (0 const, 1 work; bit8 divisor) | 1,2 table offset | 3 n_ev
+               | 4 ev_off (words from step start) | 5 0 | strides over out axes[A] | strides over sum axes[S]
+  evidence pair: (slot, stride)
+  segment record[8]: 0,1 work offset | 2 size | 3 out offset | 4 flags (bit0 normalise) | 5,6,7 0
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Hashable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+MAGIC = 0x50475831
+VERSION = 1
+HEADER_WORDS = 16
+STEP_FIXED = 12
+OP_FIXED = 6
+SEG_WORDS = 8
+MAX_OPS = 16  # operands per step the kernels are compiled for; larger products are split by the builder
+MAX_AXES = 24  # out axes + sum axes per step after coalescing
+
+KIND_CONST = 0
+KIND_WORK = 1
+FLAG_MAX = 1
+FLAG_DIV = 2
+SEG_NORMALIZE = 1
+
+
+def _lohi(x: int) -> Tuple[int, int]:
+    x = int(x)
+    lo = x & 0xFFFFFFFF
+    hi = (x >> 32) & 0xFFFFFFFF
+    return (lo - (1 << 32) if lo >= (1 << 31) else lo, hi - (1 << 32) if hi >= (1 << 31) else hi)
+
+
+def lohi_to_int(lo: int, hi: int) -> int:
+    return (int(hi) << 32) | (int(lo) & 0xFFFFFFFF)
+
+
+@dataclass
+class Table:
+    """A dense table over `vars` (C-order). kind const -> offset into the blob; work -> workspace."""
+
+    kind: int
+    vars: Tuple[Hashable, ...]
+    dims: Tuple[int, ...]
+    offset: int = -1  # entries; work tables get theirs in finalize()
+    tid: int = -1
+    first_step: int = -1
+    last_step: int = -1
+
+    @property
+    def size(self) -> int:
+        s = 1
+        for d in self.dims:
+            s *= int(d)
+        return s
+
+
+@dataclass
+class StepSpec:
+    out: Table
+    sum_vars: Tuple[Hashable, ...]
+    operands: List[Tuple[Table, bool]]  # (table, is_divisor)
+    reduce_max: bool = False
+    level: int = 0
+
+
+@dataclass
+class Segment:
+    table: Table
+    out_offset: int
+    normalize: bool
+    vars: Tuple[Hashable, ...] = ()
+
+
+@dataclass
+class Plan:
+    pool: np.ndarray  # int32
+    const_blob: np.ndarray  # float64
+    ev_vars: Tuple[Hashable, ...]
+    segments: List[Segment]
+    out_elems: int
+    ws_entries: int
+    n_steps: int
+    card: Dict[Hashable, int]
+    steps: List[StepSpec] = field(default_factory=list, repr=False)
+    meta: dict = field(default_factory=dict)
+
+    def algorithmic_bytes(self, batch: int, itemsize: int = 8) -> int:
+        """every tensor counted once per step in which it is an operand or result,
+        batch-invariant operands once per step, plus evidence in and posteriors out."""
+        total = 0
+        for st in self.steps:
+            work = st.out.size
+            const = 0
+            for t, _ in st.operands:
+                if t.kind == KIND_WORK:
+                    work += t.size
+                else:
+                    const += t.size
+            total += itemsize * (batch * work + const)
+        total += 4 * batch * len(self.ev_vars) + itemsize * batch * self.out_elems
+        return total
+
+    def flops(self, batch: int) -> int:
+        f = 0
+        for st in self.steps:
+            joint = st.out.size
+            for v in st.sum_vars:
+                joint *= self.card[v]
+            f += joint * max(1, len(st.operands))
+        return f * batch
+
+
+class PlanBuilder:
+    """Collects tables and steps, then assigns workspace offsets by liveness and packs the pool."""
+
+    def __init__(self, card: Dict[Hashable, int], ev_vars: Sequence[Hashable]):
+        self.card = {v: int(c) for v, c in card.items()}
+        self.ev_vars = tuple(ev_vars)
+        self.ev_slot = {v: i for i, v in enumerate(self.ev_vars)}
+        self.tables: List[Table] = []
+        self.steps: List[StepSpec] = []
+        self.segments: List[Segment] = []
+        self._const_chunks: List[np.ndarray] = []
+        self._const_len = 0
+        self._const_cache: Dict[int, Table] = {}
+
+    # ---- tables ----------------------------------------------------------------------------
+    def add_const(self, vars_: Sequence[Hashable], values: np.ndarray, key=None) -> Table:
+        if key is not None and key in self._const_cache:
+            return self._const_cache[key]
+        vars_ = tuple(vars_)
+        dims = tuple(self.card[v] for v in vars_)
+        values = np.ascontiguousarray(np.asarray(values, dtype=np.float64))
+        if values.size != int(np.prod(dims, dtype=np.int64)):
+            raise ValueError("const table size does not match its scope")
+        t = Table(KIND_CONST, vars_, dims, offset=self._const_len, tid=len(self.tables))
+        self._const_chunks.append(values.reshape(-1))
+        # keep every table 16-byte aligned for both dtypes
+        pad = (-values.size) % 4
+        if pad:
+            self._const_chunks.append(np.zeros(pad))
+        self._const_len += values.size + pad
+        self.tables.append(t)
+        if key is not None:
+            self._const_cache[key] = t
+        return t
+
+    def new_work(self, vars_: Sequence[Hashable]) -> Table:
+        vars_ = tuple(vars_)
+        for v in vars_:
+            if v in self.ev_slot:
+                raise ValueError(f"work table scope may not contain evidence variable {v}")
+        t = Table(KIND_WORK, vars_, tuple(self.card[v] for v in vars_), tid=len(self.tables))
+        self.tables.append(t)
+        return t
+
+    # ---- steps -----------------------------------------------------------------------------
+    def contract(
+        self,
+        operands: Sequence[Table],
+        out_vars: Sequence[Hashable],
+        divisors: Sequence[Table] = (),
+        reduce_max: bool = False,
+        level: int = 0,
+    ) -> Table:
+        """out[out_vars] = reduce over every other non-evidence variable of prod(operands) / prod(divisors)."""
+        out_vars = tuple(out_vars)
+        ops = list(operands)
+        # split wide products so that no step exceeds MAX_OPS operands (divisors count)
+        while len(ops) + len(divisors) > MAX_OPS:
+            take = MAX_OPS
+            ops.sort(key=lambda t: t.size)
+            group, ops = ops[:take], ops[take:]
+            scope = []
+            for t in group:
+                for v in t.vars:
+                    if v not in self.ev_slot and v not in scope:
+                        scope.append(v)
+            # variables that appear nowhere else may be reduced right here
+            later = set(out_vars)
+            for t in list(ops) + list(divisors):
+                later |= set(t.vars)
+            keep = [v for v in scope if v in later]
+            ops.append(self.contract(group, keep, reduce_max=reduce_max, level=level))
+        scope = []
+        for t in ops:
+            for v in t.vars:
+                if v not in self.ev_slot and v not in scope:
+                    scope.append(v)
+        for v in out_vars:
+            if v not in scope:
+                raise ValueError(f"output variable {v} is not in any operand")
+        for d in divisors:
+            for v in d.vars:
+                if v not in self.ev_slot and v not in out_vars:
+                    raise ValueError("divisor scope must be within the output scope")
+        sum_vars = tuple(v for v in scope if v not in out_vars)
+        out = self.new_work(out_vars)
+        idx = len(self.steps)
+        self.steps.append(
+            StepSpec(out, sum_vars, [(t, False) for t in ops] + [(t, True) for t in divisors], reduce_max, level)
+        )
+        out.first_step = idx
+        for t in list(ops) + list(divisors):
+            if t.kind == KIND_WORK:
+                t.last_step = max(t.last_step, idx)
+        return out
+
+    def emit(self, table: Table, normalize: bool, vars_: Sequence[Hashable] = None) -> Segment:
+        if table.kind != KIND_WORK:
+            raise ValueError("only work tables can be emitted")
+        off = sum(s.table.size for s in self.segments)
+        seg = Segment(table, off, normalize, tuple(vars_ if vars_ is not None else table.vars))
+        self.segments.append(seg)
+        table.last_step = 1 << 60  # alive until the output pass
+        return seg
+
+    # ---- lowering --------------------------------------------------------------------------
+    def _strides(self, t: Table) -> Dict[Hashable, int]:
+        st = {}
+        acc = 1
+        for v, d in zip(reversed(t.vars), reversed(t.dims)):
+            st[v] = acc
+            acc *= d
+        return st
+
+    def _lower_step(self, st: StepSpec) -> List[int]:
+        out_vars = [v for v in st.out.vars]
+        out_dims = [self.card[v] for v in out_vars]
+        sum_vars = list(st.sum_vars)
+        sum_dims = [self.card[v] for v in sum_vars]
+        per_op = []
+        for t, is_div in st.operands:
+            strides = self._strides(t)
+            so = [strides.get(v, 0) for v in out_vars]
+            ss = [strides.get(v, 0) for v in sum_vars]
+            ev = [(self.ev_slot[v], strides[v]) for v in t.vars if v in self.ev_slot]
+            for v in t.vars:
+                if v not in self.ev_slot and v not in out_vars and v not in sum_vars:
+                    raise AssertionError("operand variable not covered by the step")
+            per_op.append((t, is_div, so, ss, ev))
+
+        def coalesce(dims, cols):
+            """merge adjacent axes (i, i+1) when every operand walks them contiguously; drop extent-1 axes"""
+            keep = [i for i, d in enumerate(dims) if d != 1]
+            dims = [dims[i] for i in keep]
+            cols = [[c[i] for i in keep] for c in cols]
+            i = 0
+            while i + 1 < len(dims):
+                if all(c[i] == c[i + 1] * dims[i + 1] for c in cols):
+                    dims[i] = dims[i] * dims[i + 1]
+                    del dims[i + 1]
+                    for c in cols:
+                        c[i] = c[i + 1]
+                        del c[i + 1]
+                else:
+                    i += 1
+            return dims, cols
+
+        # the output itself is an (implicit) operand of the out axes: row-major contiguous
+        out_self = []
+        acc = 1
+        for d in reversed(out_dims):
+            out_self.insert(0, acc)
+            acc *= d
+        odims, ocols = coalesce(out_dims, [p[2] for p in per_op] + [out_self])
+        ocols = ocols[:-1]
+        sdims, scols = coalesce(sum_dims, [p[3] for p in per_op])
+        A, S, K = len(odims), len(sdims), len(per_op)
+        if A + S > MAX_AXES:
+            raise ValueError(f"step needs {A + S} axes > MAX_AXES={MAX_AXES}")
+        out_size = st.out.size
+        sum_size = 1
+        for d in sum_dims:
+            sum_size *= d
+        flags = (FLAG_MAX if st.reduce_max else 0) | (FLAG_DIV if any(p[1] for p in per_op) else 0)
+        rec = [A, S, K, flags, *_lohi(out_size), *_lohi(sum_size), *_lohi(st.out.offset), st.level, 0]
+        rec += odims + sdims
+        op_words = OP_FIXED + A + S
+        ev_base = STEP_FIXED + A + S + K * op_words
+        ev_words: List[int] = []
+        for k, (t, is_div, _, _, ev) in enumerate(per_op):
+            kind = t.kind | (0x100 if is_div else 0)
+            rec += [kind, *_lohi(t.offset), len(ev), ev_base + len(ev_words), 0]
+            rec += ocols[k] + scols[k]
+            for slot, stride in ev:
+                ev_words += [slot, stride]
+        rec += ev_words
+        return rec
+
+    def finalize(self, meta: Optional[dict] = None) -> Plan:
+        # liveness-based first-fit allocation of work tables (steps run in order on one stream)
+        n_steps = len(self.steps)
+        work = [t for t in self.tables if t.kind == KIND_WORK and t.first_step >= 0]
+        for t in work:
+            if t.last_step < 0:
+                t.last_step = t.first_step
+        by_birth = sorted(work, key=lambda t: t.first_step)
+        free: List[Tuple[int, int]] = []  # (offset, size), kept sorted by offset
+        live: List[Table] = []
+        top = 0
+        ALIGN = 1
+
+        def release(t):
+            nonlocal free
+            free.append((t.offset, t.size))
+            free.sort()
+            merged = []
+            for off, sz in free:
+                if merged and merged[-1][0] + merged[-1][1] == off:
+                    merged[-1] = (merged[-1][0], merged[-1][1] + sz)
+                else:
+                    merged.append((off, sz))
+            free = merged
+
+        for t in by_birth:
+            # a step may not write a table overlapping one of its own operands: free only tables whose
+            # last use is strictly before this step
+            still = []
+            for l in live:
+                if l.last_step < t.first_step:
+                    release(l)
+                else:
+                    still.append(l)
+            live = still
+            need = max(1, t.size)
+            placed = False
+            for i, (off, sz) in enumerate(free):
+                if sz >= need:
+                    t.offset = off
+                    if sz == need:
+                        free.pop(i)
+                    else:
+                        free[i] = (off + need, sz - need)
+                    placed = True
+                    break
+            if not placed:
+                if free and free[-1][0] + free[-1][1] == top:
+                    off, sz = free.pop()
+                    t.offset = off
+                    top = off + need
+                else:
+                    t.offset = top
+                    top += need
+            live.append(t)
+        ws_entries = max(1, top)
+
+        step_recs = [self._lower_step(st) for st in self.steps]
+        out_elems = sum(s.table.size for s in self.segments)
+        max_ops = max([len(st.operands) for st in self.steps], default=0)
+        max_axes = max([r[0] + r[1] for r in step_recs], default=0)
+        const_len = max(self._const_len, 1)
+        header = [MAGIC, VERSION, len(self.ev_vars), n_steps, len(self.segments), out_elems]
+        header += [*_lohi(ws_entries), *_lohi(const_len)]
+        step_index_off = HEADER_WORDS
+        pos = step_index_off + n_steps
+        index = []
+        for r in step_recs:
+            index.append(pos)
+            pos += len(r)
+        segs_off = pos
+        header += [step_index_off, segs_off, max_ops, max_axes, 0, 0]
+        words = header + index
+        for r in step_recs:
+            words += r
+        for s in self.segments:
+            words += [*_lohi(s.table.offset), s.table.size, s.out_offset, SEG_NORMALIZE if s.normalize else 0, 0, 0, 0]
+        pool = np.array(words, dtype=np.int64)
+        if pool.max(initial=0) >= (1 << 31) or pool.min(initial=0) < -(1 << 31):
+            raise ValueError("plan word does not fit int32")
+        blob = np.concatenate(self._const_chunks) if self._const_chunks else np.zeros(1)
+        return Plan(
+            pool=pool.astype(np.int32),
+            const_blob=np.ascontiguousarray(blob, dtype=np.float64),
+            ev_vars=self.ev_vars,
+            segments=list(self.segments),
+            out_elems=out_elems,
+            ws_entries=ws_entries,
+            n_steps=n_steps,
+            card=dict(self.card),
+            steps=list(self.steps),
+            meta=dict(meta or {}),
+        )

@@ -1,0 +1,485 @@
+"""Plan compiler: model (+ query/evidence signature) -> static contraction plan (pgmpy_b200.plan.Plan).
+
+Runs once per model / per signature on the host. Two plan families, matching the two closed forms the
+reference computes:
+
+  * VE mode  (`compile_ve_plan`, prune=True): normalise( sum_{K \\ (Q u E)} prod_{v in K} CPT'_v[E=e] ), K = kept
+    nodes of Inference._prune_bayesian_model (pgmpy/inference/base.py:154-212), CPT'_v = CPT with the
+    dropped parents summed out and columns renormalised (pgmpy/factors/discrete/CPD.py:483-524).
+    Steps follow the elimination loop of VariableElimination._variable_elimination
+    (pgmpy/inference/ExactInference.py:200-229) with OUR min-fill order, each step fused product+sum-out.
+  * BP mode  (`compile_jt_plan`, or compile_ve_plan(prune=False)): all factors, no pruning — what
+    BeliefPropagation.calibrate/query computes (ExactInference.py:854-895, :997-1111). The junction tree
+    is ours (min-fill); message passing is a two-pass collect/distribute schedule whose messages are
+    fused product+sum-out steps over the clique potential and the incoming messages.
+"""
+from __future__ import annotations
+
+from typing import Dict, Hashable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import graph as G
+from .factors import DiscreteFactor, TabularCPD
+from .models import DiscreteBayesianNetwork, JunctionTree
+from .plan import Plan, PlanBuilder, Table
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side constant folding (batch-invariant, once per plan)
+# ---------------------------------------------------------------------------------------------
+def _product_tables(tables: Sequence[Tuple[Sequence[Hashable], np.ndarray]], out_vars: Sequence[Hashable]) -> np.ndarray:
+    """Dense product of constant tables over `out_vars` (used to build clique potentials once per model,
+    as the reference does at pgmpy/models/DiscreteMarkovNetwork.py:598-629)."""
+    idx = {v: i for i, v in enumerate(out_vars)}
+    dims = {}
+    args = []
+    for vars_, vals in tables:
+        args += [vals, [idx[v] for v in vars_]]
+        for v, d in zip(vars_, np.shape(vals)):
+            dims[v] = d
+    if not args:
+        return np.ones(())
+    present = [v for v in out_vars if v in dims]
+    prod = np.einsum(*args, [idx[v] for v in present], optimize=False)
+    # broadcast over clique variables that no assigned table mentions
+    shape = [dims.get(v, 1) for v in out_vars]
+    return prod.reshape(shape)
+
+
+def marginalized_cpd(cpd: TabularCPD, drop: Sequence[Hashable]) -> Tuple[List[Hashable], np.ndarray]:
+    """CPT with parents `drop` summed out and columns renormalised — what the reference's pruning does
+    to CPDs whose scope leaves the kept set (base.py:203-208 -> CPD.py:483-524: sum, then
+    `cpd / cpd.sum(axis=0)` on the 2-D view)."""
+    keep_axes = [i for i, v in enumerate(cpd.variables) if v not in drop]
+    vals = np.einsum(cpd.values, list(range(len(cpd.variables))), keep_axes)
+    two_d = vals.reshape(vals.shape[0], -1)
+    two_d = two_d / two_d.sum(axis=0)
+    return [cpd.variables[i] for i in keep_axes], two_d.reshape(vals.shape)
+
+
+# ---------------------------------------------------------------------------------------------
+# junction tree of a Bayesian network (ours)
+# ---------------------------------------------------------------------------------------------
+def jt_structure(model: DiscreteBayesianNetwork):
+    nodes = model.nodes()
+    rank = {v: i for i, v in enumerate(nodes)}
+    card = model.get_cardinality()
+    parents = {n: model.get_parents(n) for n in nodes}
+    adj = G.moral_graph(parents)
+    cliques, edges = G.junction_tree(adj, card, rank)
+    return cliques, edges
+
+
+def assign_factors(cliques: Sequence[Tuple[Hashable, ...]], scopes: Sequence[Sequence[Hashable]], card) -> List[int]:
+    """Each factor goes to the smallest clique containing its scope (every factor used exactly once)."""
+    sets = [set(c) for c in cliques]
+    sizes = [int(np.prod([card[v] for v in c], dtype=np.int64)) for c in cliques]
+    by_var: Dict[Hashable, List[int]] = {}
+    for i, c in enumerate(cliques):
+        for v in c:
+            by_var.setdefault(v, []).append(i)
+    out = []
+    for sc in scopes:
+        sc = list(sc)
+        cand = by_var[sc[0]]
+        best = None
+        for i in cand:
+            if all(v in sets[i] for v in sc):
+                if best is None or sizes[i] < sizes[best]:
+                    best = i
+        if best is None:
+            raise ValueError(f"no clique contains factor scope {sc}")
+        out.append(best)
+    return out
+
+
+def build_junction_tree(model: DiscreteBayesianNetwork) -> JunctionTree:
+    """Min-fill junction tree with clique potentials = product of the assigned CPDs (ones where none),
+    the same object shape BeliefPropagation.__init__ accepts (ExactInference.py:742-745)."""
+    cliques, edges = jt_structure(model)
+    card = model.get_cardinality()
+    states = model.states
+    cpds = model.get_cpds()
+    owner = assign_factors(cliques, [c.variables for c in cpds], card)
+    jt = JunctionTree()
+    jt.add_nodes_from(cliques)
+    for a, b in edges:
+        if set(cliques[a]) & set(cliques[b]):
+            jt.add_edge(cliques[a], cliques[b])
+    for i, c in enumerate(cliques):
+        mine = [(cpd.variables, cpd.values) for cpd, o in zip(cpds, owner) if o == i]
+        dims = [card[v] for v in c]
+        vals = np.ones(dims) * _product_tables(mine, c) if mine else np.ones(dims)
+        jt.factors.append(DiscreteFactor(list(c), dims, vals, {v: states[v] for v in c}))
+    return jt
+
+
+# ---------------------------------------------------------------------------------------------
+# VE plans
+# ---------------------------------------------------------------------------------------------
+def _pruned_factors(model: DiscreteBayesianNetwork, variables, evidence_vars, prune: bool):
+    nodes = model.nodes()
+    if prune:
+        parents = {n: model.get_parents(n) for n in nodes}
+        children = {n: model.get_children(n) for n in nodes}
+        kept = G.prune_nodes(parents, children, list(variables), list(evidence_vars))
+    else:
+        kept = set(nodes)
+    factors = []
+    for v in nodes:
+        if v not in kept:
+            continue
+        cpd = model.get_cpds(v)
+        drop = [p for p in cpd.variables[1:] if p not in kept]
+        if drop:
+            vars_, vals = marginalized_cpd(cpd, drop)
+        else:
+            vars_, vals = list(cpd.variables), cpd.values
+        factors.append((tuple(vars_), vals, ("cpd", v, tuple(drop))))
+    return kept, factors
+
+
+def compile_factor_ve_plan(
+    factors: Sequence[Tuple[Sequence[Hashable], np.ndarray, object]],
+    card: Dict[Hashable, int],
+    variables: Sequence[Hashable],
+    evidence_vars: Sequence[Hashable],
+    joint: bool = True,
+    normalize: bool = True,
+    elimination_order: Optional[Sequence[Hashable]] = None,
+    rank: Optional[Dict[Hashable, int]] = None,
+    meta: Optional[dict] = None,
+) -> Plan:
+    """Sum-product variable elimination over an explicit factor list.
+
+    `factors` = (scope, values, key). Factors whose whole scope is observed are dropped, as both
+    reference paths do (greedy: ExactInference.py:383-384; classic: scalar factors fall out of
+    `working_factors`, :53-66). Output: the joint over `variables` in the caller's order
+    (ExactInference.py:404-414), or one marginal per variable when joint=False (:424-433)."""
+    variables = list(variables)
+    ev = list(evidence_vars)
+    evset = set(ev)
+    b = PlanBuilder(card, ev)
+    work: List[Table] = []
+    for scope, vals, key in factors:
+        if all(v in evset for v in scope):
+            continue
+        work.append(b.add_const(scope, vals, key=None))
+    free_scopes = [[v for v in t.vars if v not in evset] for t in work]
+    present = set(v for sc in free_scopes for v in sc)
+    for q in variables:
+        if q not in present:
+            raise ValueError(f"query variable {q} not in any factor")
+    if elimination_order is None:
+        adj = G.interaction_graph(free_scopes)
+        if rank is None:
+            rank = {v: i for i, v in enumerate(sorted(adj, key=str))}
+        order, _ = G.min_fill_order(adj, card, keep=variables, rank={v: rank.get(v, 0) for v in adj})
+    else:
+        order = [v for v in elimination_order if v in present and v not in variables]
+        missing = present - set(order) - set(variables)
+        if missing:
+            raise ValueError(f"elimination order misses variables: {sorted(map(str, missing))}")
+    level = 0
+    for var in order:
+        touching = [t for t in work if var in t.vars]
+        if not touching:
+            continue
+        work = [t for t in work if var not in t.vars]
+        scope: List[Hashable] = []
+        biggest = max(touching, key=lambda t: t.size)
+        for t in [biggest] + touching:
+            for v in t.vars:
+                if v not in evset and v != var and v not in scope:
+                    scope.append(v)
+        out = b.contract(touching, scope, level=level)
+        level += 1
+        work.append(out)
+    # every remaining factor has scope within `variables`
+    joint_t = b.contract(work, variables, level=level)
+    if joint:
+        b.emit(joint_t, normalize, variables)
+    else:
+        for q in variables:
+            if len(variables) == 1:
+                b.emit(joint_t, normalize, [q])
+            else:
+                m = b.contract([joint_t], [q], level=level + 1)
+                b.emit(m, normalize, [q])
+    m = {"mode": "ve", "variables": tuple(variables), "evidence_vars": tuple(ev), "joint": joint, "order": tuple(order)}
+    m.update(meta or {})
+    return b.finalize(m)
+
+
+def compile_ve_plan(
+    model: DiscreteBayesianNetwork,
+    variables: Sequence[Hashable],
+    evidence_vars: Sequence[Hashable] = (),
+    joint: bool = True,
+    prune: bool = True,
+    elimination_order: Optional[Sequence[Hashable]] = None,
+) -> Plan:
+    kept, factors = _pruned_factors(model, variables, evidence_vars, prune)
+    ev = [v for v in evidence_vars]  # all evidence variables survive pruning (base.py:192-194)
+    rank = {v: i for i, v in enumerate(model.nodes())}
+    return compile_factor_ve_plan(
+        factors,
+        model.get_cardinality(),
+        variables,
+        ev,
+        joint=joint,
+        normalize=True,
+        elimination_order=elimination_order,
+        rank=rank,
+        meta={"kept": tuple(sorted(kept, key=lambda v: rank[v])), "prune": prune},
+    )
+
+
+# ---------------------------------------------------------------------------------------------
+# junction-tree (BP mode) plans
+# ---------------------------------------------------------------------------------------------
+class JTStructure:
+    """Rooted junction tree + clique potentials, built once per model and shared by all signatures."""
+
+    def __init__(self, cliques, edges, potentials, card, states):
+        self.cliques = [tuple(c) for c in cliques]
+        self.potentials = potentials  # list of ndarray shaped by clique dims
+        self.card = dict(card)
+        self.states = states
+        n = len(self.cliques)
+        self.nb: List[List[int]] = [[] for _ in range(n)]
+        for a, b in edges:
+            self.nb[a].append(b)
+            self.nb[b].append(a)
+        self.edges = [tuple(e) for e in edges]
+        self.root = self._centre()
+        self.parent = [-1] * n
+        self.depth = [0] * n
+        self.pre: List[int] = []
+        stack = [self.root]
+        seen = {self.root}
+        while stack:
+            x = stack.pop()
+            self.pre.append(x)
+            for y in self.nb[x]:
+                if y not in seen:
+                    seen.add(y)
+                    self.parent[y] = x
+                    self.depth[y] = self.depth[x] + 1
+                    stack.append(y)
+        if len(self.pre) != n:
+            raise ValueError("junction tree is not connected")
+        self.children = [[y for y in self.nb[x] if self.parent[y] == x] for x in range(n)]
+        self.height = [0] * n
+        for x in reversed(self.pre):
+            for y in self.children[x]:
+                self.height[x] = max(self.height[x], self.height[y] + 1)
+
+    def _centre(self) -> int:
+        n = len(self.cliques)
+        if n == 1:
+            return 0
+
+        def far(src):
+            dist = {src: 0}
+            order = [src]
+            for x in order:
+                for y in self.nb[x]:
+                    if y not in dist:
+                        dist[y] = dist[x] + 1
+                        order.append(y)
+            last = order[-1]
+            return last, dist
+
+        a, _ = far(0)
+        b, da = far(a)
+        _, db = far(b)
+        diam = da[b]
+        best = min(range(n), key=lambda x: (max(da.get(x, n), db.get(x, n)), x))
+        return best
+
+    @classmethod
+    def from_model(cls, model: DiscreteBayesianNetwork) -> "JTStructure":
+        cliques, edges = jt_structure(model)
+        card = model.get_cardinality()
+        cpds = model.get_cpds()
+        owner = assign_factors(cliques, [c.variables for c in cpds], card)
+        pots = []
+        for i, c in enumerate(cliques):
+            mine = [(cpd.variables, cpd.values) for cpd, o in zip(cpds, owner) if o == i]
+            dims = [card[v] for v in c]
+            pots.append(np.ones(dims) * _product_tables(mine, c) if mine else np.ones(dims))
+        return cls(cliques, edges, pots, card, model.states)
+
+    @classmethod
+    def from_junction_tree(cls, jt: JunctionTree) -> "JTStructure":
+        cliques = jt.nodes()
+        index = {c: i for i, c in enumerate(cliques)}
+        edges = [(index[tuple(u)], index[tuple(v)]) for u, v in jt.edges()]
+        card = jt.get_cardinality()
+        pots = []
+        for c in cliques:
+            f = jt.get_factors(c)
+            perm = [f.variables.index(v) for v in c]
+            pots.append(np.ascontiguousarray(np.transpose(f.values, perm)))
+        # join a forest with empty-sepset edges
+        comp = list(range(len(cliques)))
+
+        def cf(i):
+            while comp[i] != i:
+                comp[i] = comp[comp[i]]
+                i = comp[i]
+            return i
+
+        for a, b in edges:
+            comp[cf(a)] = cf(b)
+        reps = sorted({cf(i) for i in range(len(cliques))})
+        for k in range(1, len(reps)):
+            edges.append((reps[0], reps[k]))
+        return cls(cliques, edges, pots, card, jt.states)
+
+
+def compile_jt_plan(
+    jt: JTStructure,
+    evidence_vars: Sequence[Hashable] = (),
+    variables: Optional[Sequence[Hashable]] = None,
+    normalize: bool = True,
+    emit_beliefs: bool = False,
+    distribute: str = "auto",
+) -> Plan:
+    """Two-pass message passing on the rooted junction tree for one evidence-variable signature.
+
+      collect    (leaves -> root):  m[i->p] = sum_{C_i \\ S_ip} psi_i[E=e] * prod_{c in ch(i)} m[c->i]
+      distribute (root -> leaves):  m[p->c] = sum_{C_p \\ S_pc} psi_p[E=e] * prod_{n in nb(p) \\ c} m[n->p]
+                       or, for cliques of degree >= 3 ("divide"):  beta_p = psi_p * prod_n m[n->p],
+                       m[p->c] = (sum_{C_p \\ S_pc} beta_p) / m[c->p]   with 0/0 -> 0  — the reference's
+                       belief-update rule sigma / mu (ExactInference.py:788-805, DiscreteFactor.py:859-863)
+      marginals: P(v, e) from the cheapest sepset or clique holding v, normalised per variable.
+
+    `variables=None` means every unobserved variable of the tree (all-marginals query).
+    `emit_beliefs=True` emits the calibrated clique beliefs and sepset beliefs instead (un-normalised,
+    like get_clique_beliefs/get_sepset_beliefs, :750-768)."""
+    ev = list(evidence_vars)
+    evset = set(ev)
+    card = jt.card
+    b = PlanBuilder(card, ev)
+    n = len(jt.cliques)
+    free = [tuple(v for v in c if v not in evset) for c in jt.cliques]
+    psi = [b.add_const(jt.cliques[i], jt.potentials[i]) for i in range(n)]
+
+    def sep(i, j):
+        sj = set(jt.cliques[j])
+        return tuple(v for v in free[i] if v in sj)
+
+    def fsize(vars_):
+        s = 1
+        for v in vars_:
+            s *= card[v]
+        return s
+
+    up: Dict[int, Table] = {}
+    # collect: children before parents
+    for i in reversed(jt.pre):
+        p = jt.parent[i]
+        if p < 0:
+            continue
+        ops = [psi[i]] + [up[c] for c in jt.children[i]]
+        up[i] = b.contract(ops, sep(i, p), level=jt.height[i])
+    base_level = max(jt.height) + 1
+    down: Dict[int, Table] = {}
+    belief: Dict[int, Table] = {}
+
+    def incoming(i, exclude=None):
+        ops = [up[c] for c in jt.children[i] if c != exclude]
+        if jt.parent[i] >= 0 and jt.parent[i] != exclude:
+            ops.append(down[i])
+        return ops
+
+    def want_belief(i):
+        if emit_beliefs:
+            return True
+        if distribute == "ss":
+            return False
+        if distribute == "divide":
+            return len(jt.children[i]) >= 1
+        return len(jt.nb[i]) >= 3 and len(jt.children[i]) >= 2
+
+    for i in jt.pre:
+        lvl = base_level + 2 * jt.depth[i]
+        if want_belief(i):
+            belief[i] = b.contract([psi[i]] + incoming(i), free[i], level=lvl)
+        for c in jt.children[i]:
+            if i in belief:
+                down[c] = b.contract([belief[i]], sep(i, c), divisors=[up[c]], level=lvl + 1)
+            else:
+                down[c] = b.contract([psi[i]] + incoming(i, exclude=c), sep(i, c), level=lvl + 1)
+    final_level = base_level + 2 * (max(jt.depth) + 1)
+
+    if emit_beliefs:
+        for i in range(n):
+            b.emit(belief[i], False, free[i])
+        for i in range(n):
+            p = jt.parent[i]
+            if p >= 0:
+                # sepset belief mu_ip = m[i->p] * m[p->i]
+                mu = b.contract([up[i], down[i]], sep(i, p), level=final_level)
+                b.emit(mu, False, sep(i, p))
+        return b.finalize({"mode": "jt-beliefs", "evidence_vars": tuple(ev), "root": jt.root})
+
+    if variables is None:
+        seen = set()
+        variables = []
+        for c in jt.cliques:
+            for v in c:
+                if v not in evset and v not in seen:
+                    seen.add(v)
+                    variables.append(v)
+    variables = list(variables)
+    holders: Dict[Hashable, List[int]] = {}
+    for i, c in enumerate(free):
+        for v in c:
+            holders.setdefault(v, []).append(i)
+    for v in variables:
+        if v in evset:
+            raise ValueError(f"{v} is observed")
+        if v not in holders:
+            raise ValueError(f"variable {v} is not in the junction tree")
+        best = None  # (cost, kind, clique)
+        for i in holders[v]:
+            cost = fsize(free[i]) * (1 if i in belief else 1 + len(jt.nb[i]))
+            cand = (cost, 0, i)
+            if best is None or cand < best:
+                best = cand
+            p = jt.parent[i]
+            if p >= 0 and v in jt.cliques[p]:
+                cand = (fsize(sep(i, p)) * 2, 1, i)
+                if cand < best:
+                    best = cand
+        _, kind, i = best
+        if kind == 1:
+            t = b.contract([up[i], down[i]], [v], level=final_level)
+        elif i in belief:
+            t = b.contract([belief[i]], [v], level=final_level)
+        else:
+            t = b.contract([psi[i]] + incoming(i), [v], level=final_level)
+        b.emit(t, normalize, [v])
+    return b.finalize(
+        {"mode": "jt", "evidence_vars": tuple(ev), "variables": tuple(variables), "root": jt.root, "n_cliques": n}
+    )
+
+
+# ---------------------------------------------------------------------------------------------
+# evidence state mapping (bit-exact with pgmpy/utils/state_name.py:71-84)
+# ---------------------------------------------------------------------------------------------
+def evidence_to_states(states: Dict[Hashable, list], ev_vars: Sequence[Hashable], evidence_rows) -> np.ndarray:
+    """List of {var: state_name} dicts -> int32 [B, k] state indices in `ev_vars` slot order.
+    Unknown state names raise KeyError like the reference's greedy path."""
+    maps = [{name: i for i, name in enumerate(states[v])} for v in ev_vars]
+    out = np.empty((len(evidence_rows), len(ev_vars)), dtype=np.int32)
+    for r, row in enumerate(evidence_rows):
+        if set(row) != set(ev_vars):
+            raise ValueError("every evidence set of a batch must observe exactly the plan's evidence variables")
+        for j, v in enumerate(ev_vars):
+            out[r, j] = maps[j][row[v]]
+    return out
