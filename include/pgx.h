@@ -1,0 +1,122 @@
+/*
+ * pgx.h — C-ABI of libpgx.so, the B200 (sm_100a) exact-inference engine behind pgmpy's
+ * VariableElimination.query / BeliefPropagation.calibrate,query / DiscreteFactor algebra.
+ *
+ * The reference (tristantreb/pgmpy v1.0.0) is pure Python and has NO plugin/operator/FFI interface
+ * (SURVEY.md §8b): its only seam is the per-op function table pgmpy/utils/compat_fns.py:21-180 selected by
+ * pgmpy/global_vars.py:82-128. The entry points below are therefore what a binding for this path
+ * would call instead of that table: one compiled plan per (model, query signature), executed over a
+ * batch of independent evidence sets.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference/pgmpy/):
+ *   pgx_plan_create      inference/base.py:88-152 (_initialize_structures: per-variable factor index) and
+ *                        the per-query control flow of inference/ExactInference.py:141-244 (VE loop) /
+ *                        :854-895 (junction-tree calibration schedule), frozen into a static step list.
+ *   pgx_run_batch        the arithmetic of ExactInference.py:200-229 and :770-805, i.e. per step
+ *                          factors/discrete/DiscreteFactor.py:599-614  reduce   (evidence index gather)
+ *                          factors/discrete/DiscreteFactor.py:769-777  product  (einsum outer join)
+ *                          factors/discrete/DiscreteFactor.py:400-408  marginalize (einsum sum-out)
+ *                          factors/discrete/DiscreteFactor.py:838-863  divide   (0/0 -> 0, x/0 -> inf)
+ *                          factors/discrete/DiscreteFactor.py:530      normalize (NaN when the sum is 0)
+ *                        for B evidence sets at once.
+ *   pgx_evidence_reduce  DiscreteFactor.reduce (:535-617) / the greedy-path indexer ExactInference.py:355-365.
+ *   pgx_normalize        DiscreteFactor.normalize (:485-533).
+ *
+ * Conventions: plain pointers and sizes only; 0 = success, negative = error (pgx_last_error() gives the
+ * text, thread local); no exceptions cross the boundary. The CALLER owns every device buffer
+ * (table blob, evidence, output, workspace); a plan owns only device copies of its descriptors.
+ * A plan may be run concurrently on different streams with different workspaces.
+ */
+#ifndef PGX_H
+#define PGX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGX_ABI_VERSION 1
+
+/* dtype of the table blob, the workspace and the output */
+#define PGX_F64 0
+#define PGX_F32 1
+
+/* error codes */
+#define PGX_OK 0
+#define PGX_ERR_INVALID (-1)   /* malformed descriptor / argument */
+#define PGX_ERR_BOUNDS (-2)    /* a step would read or write outside its tables */
+#define PGX_ERR_WORKSPACE (-3) /* workspace too small */
+#define PGX_ERR_CUDA (-4)      /* CUDA runtime error (text in pgx_last_error) */
+#define PGX_ERR_UNSUPPORTED (-5)
+
+/* execution modes (pgx_plan_set_option(PGX_OPT_MODE, ...)) */
+#define PGX_MODE_AUTO 0     /* pick by plan size and batch */
+#define PGX_MODE_STEPWISE 1 /* one launch per step, grid over (output entries x evidence sets) */
+#define PGX_MODE_FUSED 2    /* whole plan in one launch, a warp-row of 32 evidence sets per CTA */
+
+#define PGX_OPT_MODE 1
+#define PGX_OPT_FUSED_WARPS 2 /* warps cooperating on one row of 32 evidence sets in fused mode (1..32) */
+#define PGX_OPT_USE_GRAPH 3   /* stepwise mode: replay the launch sequence as a CUDA graph (0/1) */
+
+#define PGX_INFO_N_STEPS 1
+#define PGX_INFO_OUT_ELEMS 2
+#define PGX_INFO_WS_ENTRIES 3
+#define PGX_INFO_LAST_LAUNCHES 4 /* kernels launched by the most recent pgx_run_batch */
+#define PGX_INFO_LAST_MODE 5
+#define PGX_INFO_N_EV 6
+
+typedef struct pgx_plan pgx_plan; /* opaque */
+
+typedef struct pgx_plan_desc {
+    int32_t abi_version;      /* PGX_ABI_VERSION */
+    int32_t dtype;            /* PGX_F64 | PGX_F32 */
+    const int32_t* pool;      /* HOST: plan word pool, layout in pgmpy_b200/plan.py (header, evidence cards,
+                                 step index, step records, output segments) */
+    int64_t pool_words;
+    const void* table_blob;   /* DEVICE: packed batch-invariant tables (CPTs / clique potentials), dtype above */
+    int64_t table_entries;    /* entries in table_blob */
+} pgx_plan_desc;
+
+/* Validates the pool (every operand range is bounds-checked against table_entries / the workspace size)
+ * and uploads the descriptors to the current CUDA device. */
+int pgx_plan_create(const pgx_plan_desc* desc, pgx_plan** out);
+void pgx_plan_destroy(pgx_plan* plan);
+
+/* Bytes of workspace pgx_run_batch needs for a batch of B evidence sets. */
+size_t pgx_workspace_bytes(const pgx_plan* plan, int64_t B);
+
+/* Runs the plan for B evidence sets on `stream` (a cudaStream_t; NULL = default stream).
+ *   ev_states  DEVICE int32 [B, n_ev]  state index of each evidence variable (slot order of the plan);
+ *                                      may be NULL when the plan has no evidence slots
+ *   out        DEVICE dtype [B, out_elems] posterior rows (segments normalised as the plan says)
+ * Asynchronous: returns after enqueueing. */
+int pgx_run_batch(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
+                  int64_t B, void* stream);
+
+int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value);
+int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value);
+
+/* Stand-alone batched evidence reduce (index gather):
+ *   dst[e, b] = table[ base(e) + sum_j ev_states[b, slot_j] * ev_stride_j ],  e over the free axes (row-major),
+ *   base(e) = sum_a digit_a(e) * free_stride_a.  dst layout [free entries][ldb], b fastest. */
+int pgx_evidence_reduce(int32_t dtype, const void* table, int64_t table_entries, int32_t n_free,
+                        const int32_t* free_dims, const int32_t* free_strides, int32_t n_ev, const int32_t* ev_slots,
+                        const int32_t* ev_strides, const int32_t* ev_cards, const int32_t* ev_states, int32_t ev_row_len,
+                        void* dst, int64_t B, int64_t ldb, void* stream);
+
+/* Stand-alone batched normalise: out[b, i] = src[i, b] / sum_i src[i, b]  (src layout [n][ldb]). */
+int pgx_normalize(int32_t dtype, const void* src, int64_t n, int64_t ldb, void* out, int64_t out_row_len, int64_t B,
+                  void* stream);
+
+/* Leading dimension (in evidence sets) of workspace tables for a batch of B. */
+int64_t pgx_batch_ld(int64_t B);
+
+const char* pgx_last_error(void);
+int32_t pgx_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGX_H */

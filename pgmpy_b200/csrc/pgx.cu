@@ -1,0 +1,536 @@
+// pgx.cu — CUDA kernels (sm_100a) and the C-ABI of libpgx.so (include/pgx.h).
+//
+// Kernels
+//   k_contract_step   K2: one plan step over (output entries x evidence sets); evidence gather (K1) and
+//                     divide fused into operand addressing / epilogue. HBM-bound for large tables.
+//   k_plan_fused      K5 for small models: the WHOLE plan (collect, distribute, marginals, normalise) in one
+//                     launch; a CTA owns a row of 32 evidence sets (lane = evidence set), G warps split the
+//                     output entries of each step, __syncthreads() orders dependent steps.
+//   k_emit            K4: per-segment normalise (values / values.sum(), NaN when the sum is 0) + transpose of
+//                     the [entry][b] work layout into the caller's out[b, :] rows.
+//   k_evidence_gather K1 stand-alone (DiscreteFactor.reduce for a batch).
+//   k_normalize       K4 stand-alone.
+//
+// Layout: work tables [entry][ldb], evidence set fastest => every warp access is 32 consecutive elements
+// regardless of which variable is summed; index arithmetic is warp-uniform.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pgx.h"
+#include "pgx_step.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define PGX_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(PGX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+using namespace pgx;
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+template <typename T, int MAXK>
+__global__ void __launch_bounds__(256) k_contract_step(const int32_t* __restrict__ pool, int rec_off, int rec_len,
+                                                       int ev_card_off, const T* __restrict__ cst, T* __restrict__ ws,
+                                                       const int32_t* __restrict__ ev, int n_ev, int64_t B, int64_t ldb,
+                                                       int bt_log2) {
+    extern __shared__ int32_t s_rec[];
+    for (int i = threadIdx.x; i < rec_len; i += blockDim.x) s_rec[i] = pool[rec_off + i];
+    __syncthreads();
+    const uint32_t bt_mask = (1u << bt_log2) - 1u;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = (int64_t)blockIdx.y * (bt_mask + 1u) + (t & bt_mask);
+    const uint64_t o = t >> bt_log2;
+    const uint64_t out_size = (uint64_t)ld_i64(s_rec + 4);
+    if (b >= B || o >= out_size) return;
+    const T v = contract_elem<T, MAXK>(s_rec, cst, ws, ev + b * n_ev, pool + ev_card_off, ldb, b, (uint32_t)o);
+    ws[(ld_i64(s_rec + 8) + (int64_t)o) * ldb + b] = v;
+}
+
+template <typename T>
+__device__ __forceinline__ void emit_segment(const int32_t* __restrict__ seg, const T* __restrict__ ws,
+                                             T* __restrict__ out, int64_t out_elems, int64_t ldb, int64_t b) {
+    const int64_t off = ld_i64(seg);
+    const int n = seg[2];
+    const T* src = ws + off * ldb + b;
+    T* dst = out + b * out_elems + seg[3];
+    if (seg[4] & SEG_NORMALIZE) {
+        T sum = (T)0;
+        for (int i = 0; i < n; ++i) sum += src[(int64_t)i * ldb];
+        for (int i = 0; i < n; ++i) dst[i] = src[(int64_t)i * ldb] / sum;
+    } else {
+        for (int i = 0; i < n; ++i) dst[i] = src[(int64_t)i * ldb];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_emit(const int32_t* __restrict__ pool, int segs_off, const T* __restrict__ ws,
+                                              T* __restrict__ out, int64_t out_elems, int64_t B, int64_t ldb) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    emit_segment<T>(pool + segs_off + blockIdx.y * SEG_WORDS, ws, out, out_elems, ldb, b);
+}
+
+// Whole plan in one launch. blockDim = (32, G): lane = evidence set within the row, G warps share the row.
+template <typename T, int MAXK>
+__global__ void __launch_bounds__(512) k_plan_fused(const int32_t* __restrict__ pool, const T* __restrict__ cst,
+                                                     T* __restrict__ ws, const int32_t* __restrict__ ev,
+                                                     T* __restrict__ out, int64_t B, int64_t ldb) {
+    const int n_ev = pool[2];
+    const int n_steps = pool[3];
+    const int n_segs = pool[4];
+    const int64_t out_elems = pool[5];
+    const int32_t* index = pool + pool[10];
+    const int32_t* ev_card = pool + pool[14];
+    const int G = blockDim.y;
+    const int w = threadIdx.y;
+    const int64_t b = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const bool live = b < B;
+    const int32_t* ev_row = ev + (live ? b : 0) * n_ev;
+    for (int s = 0; s < n_steps; ++s) {
+        const int32_t* rec = pool + index[s];
+        if (live) {
+            const uint32_t out_size = (uint32_t)rec[4];
+            const int64_t out_off = ld_i64(rec + 8);
+            for (uint32_t o = w; o < out_size; o += G) {
+                const T v = contract_elem_upto<T, MAXK>(rec, cst, ws, ev_row, ev_card, ldb, b, o);
+                ws[(out_off + o) * ldb + b] = v;
+            }
+        }
+        if (G > 1) __syncthreads();
+    }
+    if (live) {
+        const int32_t* segs = pool + pool[11];
+        for (int g = w; g < n_segs; g += G) emit_segment<T>(segs + g * SEG_WORDS, ws, out, out_elems, ldb, b);
+    }
+}
+
+// dst[e, b] = table[base(e) + sum_j clamp(ev[b, slot_j]) * stride_j]
+template <typename T>
+__global__ void __launch_bounds__(256) k_evidence_gather(const T* __restrict__ table, int n_free, const int32_t* dims,
+                                                         const int32_t* strides, int n_ev, const int32_t* slots,
+                                                         const int32_t* ev_strides, const int32_t* ev_cards,
+                                                         const int32_t* __restrict__ ev, int ev_row_len,
+                                                         T* __restrict__ dst, int64_t n_entries, int64_t B, int64_t ldb,
+                                                         int bt_log2) {
+    const uint32_t bt_mask = (1u << bt_log2) - 1u;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = (int64_t)blockIdx.y * (bt_mask + 1u) + (t & bt_mask);
+    const uint64_t e = t >> bt_log2;
+    if (b >= B || e >= (uint64_t)n_entries) return;
+    int64_t off = 0;
+    uint32_t rem = (uint32_t)e;
+    for (int a = n_free - 1; a >= 0; --a) {
+        const uint32_t d = (uint32_t)dims[a];
+        const uint32_t q = rem / d;
+        off += (int64_t)(rem - q * d) * strides[a];
+        rem = q;
+    }
+    for (int j = 0; j < n_ev; ++j) {
+        int32_t st = ev[b * ev_row_len + slots[j]];
+        st = st < 0 ? 0 : (st >= ev_cards[j] ? ev_cards[j] - 1 : st);
+        off += (int64_t)st * ev_strides[j];
+    }
+    dst[(int64_t)e * ldb + b] = table[off];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_normalize(const T* __restrict__ src, int64_t n, int64_t ldb, T* __restrict__ out,
+                                                   int64_t out_row_len, int64_t B) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    T sum = (T)0;
+    for (int64_t i = 0; i < n; ++i) sum += src[i * ldb + b];
+    for (int64_t i = 0; i < n; ++i) out[b * out_row_len + i] = src[i * ldb + b] / sum;
+}
+
+struct StepInfo {
+    int rec_off;
+    int rec_len;
+    int64_t out_size;
+    int64_t sum_size;
+    int n_ops;
+};
+
+int ilog2_floor(int64_t x) {
+    int l = 0;
+    while ((1LL << (l + 1)) <= x) ++l;
+    return l;
+}
+
+}  // namespace
+
+struct pgx_plan {
+    int dtype = PGX_F64;
+    int device = 0;
+    int n_ev = 0, n_steps = 0, n_segs = 0, out_elems = 0;
+    int64_t ws_entries = 0, table_entries = 0;
+    int step_index_off = 0, segs_off = 0, ev_card_off = 0, max_ops = 0;
+    std::vector<int32_t> pool;
+    std::vector<StepInfo> steps;
+    int32_t* d_pool = nullptr;
+    const void* blob = nullptr;
+    int64_t max_joint = 0;  // max over steps of out_size * sum_size
+    // options
+    int mode = PGX_MODE_AUTO;
+    int fused_warps = 0;  // 0 = auto
+    // info
+    int64_t last_launches = 0;
+    int last_mode = 0;
+};
+
+extern "C" {
+
+const char* pgx_last_error(void) { return g_err.c_str(); }
+int32_t pgx_abi_version(void) { return PGX_ABI_VERSION; }
+
+int64_t pgx_batch_ld(int64_t B) {
+    if (B <= 0) return 1;
+    if (B >= 32) return (B + 31) / 32 * 32;
+    int64_t p = 1;
+    while (p < B) p <<= 1;
+    return p;
+}
+
+int pgx_plan_create(const pgx_plan_desc* desc, pgx_plan** out) {
+    if (!desc || !out) return fail(PGX_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (desc->abi_version != PGX_ABI_VERSION) return fail(PGX_ERR_INVALID, "ABI version mismatch");
+    if (desc->dtype != PGX_F64 && desc->dtype != PGX_F32) return fail(PGX_ERR_INVALID, "unknown dtype");
+    if (!desc->pool || desc->pool_words < HEADER_WORDS) return fail(PGX_ERR_INVALID, "pool too short");
+    const int32_t* p = desc->pool;
+    const int64_t W = desc->pool_words;
+    if ((uint32_t)p[0] != MAGIC || p[1] != 1) return fail(PGX_ERR_INVALID, "bad magic/version in plan pool");
+    pgx_plan* pl = new pgx_plan();
+    pl->dtype = desc->dtype;
+    pl->n_ev = p[2];
+    pl->n_steps = p[3];
+    pl->n_segs = p[4];
+    pl->out_elems = p[5];
+    pl->ws_entries = ld_i64(p + 6);
+    pl->table_entries = desc->table_entries;
+    pl->step_index_off = p[10];
+    pl->segs_off = p[11];
+    pl->max_ops = p[12];
+    pl->ev_card_off = p[14];
+    pl->blob = desc->table_blob;
+    auto bad = [&](int code, const std::string& m) {
+        delete pl;
+        return fail(code, m);
+    };
+    if (pl->n_ev < 0 || pl->n_steps < 0 || pl->n_segs < 0 || pl->out_elems < 0 || pl->ws_entries < 1)
+        return bad(PGX_ERR_INVALID, "negative count in plan header");
+    if (ld_i64(p + 8) > desc->table_entries) return bad(PGX_ERR_BOUNDS, "table blob smaller than the plan expects");
+    if (pl->ev_card_off < HEADER_WORDS || (int64_t)pl->ev_card_off + pl->n_ev > W)
+        return bad(PGX_ERR_INVALID, "evidence cardinalities out of pool");
+    if (pl->step_index_off < HEADER_WORDS || (int64_t)pl->step_index_off + pl->n_steps > W)
+        return bad(PGX_ERR_INVALID, "step index out of pool");
+    if (pl->segs_off < HEADER_WORDS || (int64_t)pl->segs_off + (int64_t)pl->n_segs * SEG_WORDS > W)
+        return bad(PGX_ERR_INVALID, "segments out of pool");
+    if (!desc->table_blob && pl->n_steps > 0) return bad(PGX_ERR_INVALID, "null table blob");
+    const int32_t* ev_card = p + pl->ev_card_off;
+    for (int j = 0; j < pl->n_ev; ++j)
+        if (ev_card[j] < 1) return bad(PGX_ERR_INVALID, "evidence cardinality < 1");
+    for (int s = 0; s < pl->n_steps; ++s) {
+        const int64_t off = p[pl->step_index_off + s];
+        if (off < HEADER_WORDS || off + STEP_FIXED > W) return bad(PGX_ERR_INVALID, "step record out of pool");
+        const int32_t* r = p + off;
+        const int A = r[0], S = r[1], K = r[2];
+        if (A < 0 || S < 0 || A + S > MAX_AXES) return bad(PGX_ERR_UNSUPPORTED, "too many axes in a step");
+        if (K < 1 || K > MAX_OPS) return bad(PGX_ERR_UNSUPPORTED, "operand count out of range");
+        const int opw = OP_FIXED + A + S;
+        int64_t len = STEP_FIXED + A + S + (int64_t)K * opw;
+        if (off + len > W) return bad(PGX_ERR_INVALID, "step operands out of pool");
+        const int64_t out_size = ld_i64(r + 4), sum_size = ld_i64(r + 6), out_off = ld_i64(r + 8);
+        int64_t po = 1, ps = 1;
+        for (int a = 0; a < A; ++a) {
+            if (r[STEP_FIXED + a] < 1) return bad(PGX_ERR_INVALID, "axis extent < 1");
+            po *= r[STEP_FIXED + a];
+        }
+        for (int a = 0; a < S; ++a) {
+            if (r[STEP_FIXED + A + a] < 1) return bad(PGX_ERR_INVALID, "axis extent < 1");
+            ps *= r[STEP_FIXED + A + a];
+        }
+        if (po != out_size || ps != sum_size) return bad(PGX_ERR_INVALID, "axis extents disagree with sizes");
+        if (out_size < 1 || out_size >= (1LL << 31) || sum_size >= (1LL << 31))
+            return bad(PGX_ERR_UNSUPPORTED, "step index space too large");
+        if (out_off < 0 || out_off + out_size > pl->ws_entries) return bad(PGX_ERR_BOUNDS, "step output outside workspace");
+        bool seen_div = false;
+        for (int k = 0; k < K; ++k) {
+            const int32_t* op = r + STEP_FIXED + A + S + k * opw;
+            const int kind = op[0] & 0xFF;
+            const bool div = (op[0] & 0x100) != 0;
+            if (kind != 0 && kind != 1) return bad(PGX_ERR_INVALID, "unknown operand kind");
+            if (seen_div && !div) return bad(PGX_ERR_INVALID, "divisors must be the trailing operands");
+            seen_div = seen_div || div;
+            if (div && !(r[3] & FLAG_DIV)) return bad(PGX_ERR_INVALID, "divisor without FLAG_DIV");
+            const int64_t base = ld_i64(op + 1);
+            int64_t hi = base;
+            for (int a = 0; a < A; ++a) {
+                if (op[OP_FIXED + a] < 0) return bad(PGX_ERR_INVALID, "negative stride");
+                hi += (int64_t)(r[STEP_FIXED + a] - 1) * op[OP_FIXED + a];
+            }
+            for (int a = 0; a < S; ++a) {
+                if (op[OP_FIXED + A + a] < 0) return bad(PGX_ERR_INVALID, "negative stride");
+                if (div && op[OP_FIXED + A + a] != 0) return bad(PGX_ERR_INVALID, "divisor depends on a summed axis");
+                hi += (int64_t)(r[STEP_FIXED + A + a] - 1) * op[OP_FIXED + A + a];
+            }
+            const int n_ev = op[3];
+            const int64_t evo = op[4];
+            if (n_ev < 0 || (n_ev > 0 && (evo < len || off + evo + 2LL * n_ev > W)))
+                return bad(PGX_ERR_INVALID, "evidence pairs out of pool");
+            for (int j = 0; j < n_ev; ++j) {
+                const int slot = r[evo + 2 * j], stride = r[evo + 2 * j + 1];
+                if (slot < 0 || slot >= pl->n_ev || stride < 0) return bad(PGX_ERR_INVALID, "bad evidence pair");
+                hi += (int64_t)(ev_card[slot] - 1) * stride;
+            }
+            if (n_ev > 0) len = std::max<int64_t>(len, evo + 2LL * n_ev);
+            const int64_t limit = kind == 1 ? pl->ws_entries : pl->table_entries;
+            if (base < 0 || hi >= limit) return bad(PGX_ERR_BOUNDS, "operand range outside its table space");
+            if (kind == 1) {
+                // a step may not read what it writes
+                const int64_t lo = base;
+                if (!(hi < out_off || lo >= out_off + out_size))
+                    return bad(PGX_ERR_BOUNDS, "step output overlaps one of its operands");
+            }
+        }
+        pl->steps.push_back(StepInfo{(int)off, (int)len, out_size, sum_size, K});
+        pl->max_joint = std::max(pl->max_joint, out_size * std::max<int64_t>(1, sum_size));
+    }
+    int64_t out_total = 0;
+    for (int g = 0; g < pl->n_segs; ++g) {
+        const int32_t* sg = p + pl->segs_off + g * SEG_WORDS;
+        const int64_t off = ld_i64(sg);
+        if (off < 0 || sg[2] < 0 || off + sg[2] > pl->ws_entries) return bad(PGX_ERR_BOUNDS, "segment outside workspace");
+        if (sg[3] < 0 || sg[3] + sg[2] > pl->out_elems) return bad(PGX_ERR_BOUNDS, "segment outside output row");
+        out_total += sg[2];
+    }
+    (void)out_total;
+    pl->pool.assign(p, p + W);
+    cudaError_t e = cudaGetDevice(&pl->device);
+    if (e != cudaSuccess) return bad(PGX_ERR_CUDA, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
+    e = cudaMalloc((void**)&pl->d_pool, (size_t)W * sizeof(int32_t));
+    if (e != cudaSuccess) return bad(PGX_ERR_CUDA, std::string("cudaMalloc(pool): ") + cudaGetErrorString(e));
+    e = cudaMemcpy(pl->d_pool, p, (size_t)W * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(pl->d_pool);
+        return bad(PGX_ERR_CUDA, std::string("cudaMemcpy(pool): ") + cudaGetErrorString(e));
+    }
+    *out = pl;
+    return PGX_OK;
+}
+
+void pgx_plan_destroy(pgx_plan* plan) {
+    if (!plan) return;
+    if (plan->d_pool) cudaFree(plan->d_pool);
+    delete plan;
+}
+
+size_t pgx_workspace_bytes(const pgx_plan* plan, int64_t B) {
+    if (!plan || B <= 0) return 0;
+    const size_t item = plan->dtype == PGX_F64 ? 8 : 4;
+    return (size_t)plan->ws_entries * (size_t)pgx_batch_ld(B) * item;
+}
+
+int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
+    if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+    switch (option) {
+        case PGX_OPT_MODE:
+            if (value < PGX_MODE_AUTO || value > PGX_MODE_FUSED) return fail(PGX_ERR_INVALID, "unknown mode");
+            plan->mode = (int)value;
+            return PGX_OK;
+        case PGX_OPT_FUSED_WARPS:
+            if (value < 0 || value > 32) return fail(PGX_ERR_INVALID, "fused warps must be 0..32");
+            plan->fused_warps = (int)value;
+            return PGX_OK;
+        default:
+            return fail(PGX_ERR_UNSUPPORTED, "unknown option");
+    }
+}
+
+int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value) {
+    if (!plan || !value) return fail(PGX_ERR_INVALID, "null argument");
+    switch (what) {
+        case PGX_INFO_N_STEPS: *value = plan->n_steps; break;
+        case PGX_INFO_OUT_ELEMS: *value = plan->out_elems; break;
+        case PGX_INFO_WS_ENTRIES: *value = plan->ws_entries; break;
+        case PGX_INFO_LAST_LAUNCHES: *value = plan->last_launches; break;
+        case PGX_INFO_LAST_MODE: *value = plan->last_mode; break;
+        case PGX_INFO_N_EV: *value = plan->n_ev; break;
+        default: return fail(PGX_ERR_UNSUPPORTED, "unknown info key");
+    }
+    return PGX_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+template <typename T>
+int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t B, cudaStream_t st) {
+    const int64_t ldb = pgx_batch_ld(B);
+    const T* cst = (const T*)pl->blob;
+    T* ws = (T*)ws_v;
+    T* out = (T*)out_v;
+    int mode = pl->mode;
+    if (mode == PGX_MODE_AUTO) mode = (pl->max_joint <= 8192 && B >= 2048) ? PGX_MODE_FUSED : PGX_MODE_STEPWISE;
+    int64_t launches = 0;
+    if (mode == PGX_MODE_FUSED) {
+        int G = pl->fused_warps;
+        const int64_t rows = (B + 31) / 32;
+        if (G <= 0) {
+            G = (int)((148 * 16 + rows - 1) / rows);
+            if (G < 1) G = 1;
+            if (G > 16) G = 16;
+        }
+        if (G > 16) {
+            G = 16;
+        }
+        dim3 block(32, G);
+        if (pl->max_ops <= 4)
+            k_plan_fused<T, 4><<<(unsigned)rows, block, 0, st>>>(pl->d_pool, cst, ws, ev, out, B, ldb);
+        else if (pl->max_ops <= 8)
+            k_plan_fused<T, 8><<<(unsigned)rows, block, 0, st>>>(pl->d_pool, cst, ws, ev, out, B, ldb);
+        else
+            k_plan_fused<T, MAX_OPS><<<(unsigned)rows, block, 0, st>>>(pl->d_pool, cst, ws, ev, out, B, ldb);
+        PGX_CUDA(cudaGetLastError());
+        launches = 1;
+    } else {
+        const int64_t bt = ldb < 32 ? ldb : 32;
+        const int bt_log2 = ilog2_floor(bt);
+        const int64_t b_tiles = (B + bt - 1) / bt;
+        if (b_tiles > 65535) return fail(PGX_ERR_UNSUPPORTED, "batch too large for one stepwise launch (max 2,097,120)");
+        const int per_block = 256 >> bt_log2;
+        for (const StepInfo& s : pl->steps) {
+            dim3 grid((unsigned)((s.out_size + per_block - 1) / per_block), (unsigned)b_tiles);
+            const size_t smem = (size_t)s.rec_len * sizeof(int32_t);
+#define PGX_LAUNCH_STEP(MK)                                                                                      \
+    k_contract_step<T, MK><<<grid, 256, smem, st>>>(pl->d_pool, s.rec_off, s.rec_len, pl->ev_card_off, cst, ws, ev, \
+                                                    pl->n_ev, B, ldb, bt_log2)
+            if (s.n_ops <= 2)
+                PGX_LAUNCH_STEP(2);
+            else if (s.n_ops <= 4)
+                PGX_LAUNCH_STEP(4);
+            else if (s.n_ops <= 8)
+                PGX_LAUNCH_STEP(8);
+            else
+                PGX_LAUNCH_STEP(MAX_OPS);
+#undef PGX_LAUNCH_STEP
+            ++launches;
+        }
+        PGX_CUDA(cudaGetLastError());
+        if (pl->n_segs > 0) {
+            dim3 grid((unsigned)((B + 127) / 128), (unsigned)pl->n_segs);
+            if (pl->n_segs > 65535) return fail(PGX_ERR_UNSUPPORTED, "too many output segments");
+            k_emit<T><<<grid, 128, 0, st>>>(pl->d_pool, pl->segs_off, ws, out, pl->out_elems, B, ldb);
+            PGX_CUDA(cudaGetLastError());
+            ++launches;
+        }
+    }
+    pl->last_launches = launches;
+    pl->last_mode = mode;
+    return PGX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pgx_run_batch(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
+                  int64_t B, void* stream) {
+    if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+    if (B <= 0) return fail(PGX_ERR_INVALID, "batch must be positive");
+    if (plan->n_ev > 0 && !ev_states) return fail(PGX_ERR_INVALID, "plan has evidence slots but ev_states is null");
+    if (!out && plan->out_elems > 0) return fail(PGX_ERR_INVALID, "null output");
+    if (!workspace || workspace_bytes < pgx_workspace_bytes(plan, B))
+        return fail(PGX_ERR_WORKSPACE, "workspace too small: need " + std::to_string(pgx_workspace_bytes(plan, B)) + " bytes");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->dtype == PGX_F64) return run_typed<double>(plan, ev_states, out, workspace, B, st);
+    return run_typed<float>(plan, ev_states, out, workspace, B, st);
+}
+
+int pgx_evidence_reduce(int32_t dtype, const void* table, int64_t table_entries, int32_t n_free,
+                        const int32_t* free_dims, const int32_t* free_strides, int32_t n_ev, const int32_t* ev_slots,
+                        const int32_t* ev_strides, const int32_t* ev_cards, const int32_t* ev_states, int32_t ev_row_len,
+                        void* dst, int64_t B, int64_t ldb, void* stream) {
+    if (!table || !dst || B <= 0 || n_free < 0 || n_ev < 0 || n_free > MAX_AXES || n_ev > MAX_AXES)
+        return fail(PGX_ERR_INVALID, "bad argument");
+    if (n_ev > 0 && !ev_states) return fail(PGX_ERR_INVALID, "null evidence");
+    if (ldb < B) return fail(PGX_ERR_INVALID, "ldb < B");
+    int64_t n = 1, hi = 0;
+    for (int a = 0; a < n_free; ++a) {
+        if (free_dims[a] < 1 || free_strides[a] < 0) return fail(PGX_ERR_INVALID, "bad free axis");
+        n *= free_dims[a];
+        hi += (int64_t)(free_dims[a] - 1) * free_strides[a];
+    }
+    for (int j = 0; j < n_ev; ++j) {
+        if (ev_cards[j] < 1 || ev_strides[j] < 0 || ev_slots[j] < 0 || ev_slots[j] >= ev_row_len)
+            return fail(PGX_ERR_INVALID, "bad evidence axis");
+        hi += (int64_t)(ev_cards[j] - 1) * ev_strides[j];
+    }
+    if (hi >= table_entries) return fail(PGX_ERR_BOUNDS, "gather range outside the table");
+    if (n >= (1LL << 31)) return fail(PGX_ERR_UNSUPPORTED, "table too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    // small descriptor arrays go to the device once per call
+    int32_t h[6 * MAX_AXES];
+    int32_t* d = nullptr;
+    std::memset(h, 0, sizeof(h));
+    for (int a = 0; a < n_free; ++a) {
+        h[a] = free_dims[a];
+        h[MAX_AXES + a] = free_strides[a];
+    }
+    for (int j = 0; j < n_ev; ++j) {
+        h[2 * MAX_AXES + j] = ev_slots[j];
+        h[3 * MAX_AXES + j] = ev_strides[j];
+        h[4 * MAX_AXES + j] = ev_cards[j];
+    }
+    PGX_CUDA(cudaMallocAsync((void**)&d, sizeof(h), st));
+    PGX_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, st));
+    const int64_t bt = ldb < 32 ? ldb : 32;
+    const int bt_log2 = ilog2_floor(bt);
+    const int64_t b_tiles = (B + bt - 1) / bt;
+    if (b_tiles > 65535) return fail(PGX_ERR_UNSUPPORTED, "batch too large");
+    const int per_block = 256 >> bt_log2;
+    dim3 grid((unsigned)((n + per_block - 1) / per_block), (unsigned)b_tiles);
+    if (dtype == PGX_F64)
+        k_evidence_gather<double><<<grid, 256, 0, st>>>((const double*)table, n_free, d, d + MAX_AXES, n_ev,
+                                                        d + 2 * MAX_AXES, d + 3 * MAX_AXES, d + 4 * MAX_AXES, ev_states,
+                                                        ev_row_len, (double*)dst, n, B, ldb, bt_log2);
+    else
+        k_evidence_gather<float><<<grid, 256, 0, st>>>((const float*)table, n_free, d, d + MAX_AXES, n_ev,
+                                                       d + 2 * MAX_AXES, d + 3 * MAX_AXES, d + 4 * MAX_AXES, ev_states,
+                                                       ev_row_len, (float*)dst, n, B, ldb, bt_log2);
+    PGX_CUDA(cudaGetLastError());
+    PGX_CUDA(cudaFreeAsync(d, st));
+    return PGX_OK;
+}
+
+int pgx_normalize(int32_t dtype, const void* src, int64_t n, int64_t ldb, void* out, int64_t out_row_len, int64_t B,
+                  void* stream) {
+    if (!src || !out || n < 1 || B <= 0 || ldb < B || out_row_len < n) return fail(PGX_ERR_INVALID, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((B + 127) / 128);
+    if (dtype == PGX_F64)
+        k_normalize<double><<<grid, 128, 0, st>>>((const double*)src, n, ldb, (double*)out, out_row_len, B);
+    else
+        k_normalize<float><<<grid, 128, 0, st>>>((const float*)src, n, ldb, (float*)out, out_row_len, B);
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+}  // extern "C"

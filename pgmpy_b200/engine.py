@@ -1,0 +1,162 @@
+"""Device-side plan objects: upload a compiled Plan once, run it over batches of evidence sets.
+
+PyTorch is only the buffer carrier here (device memory, streams); all arithmetic happens in the
+hand-written kernels of libpgx.so. Without CUDA every entry point raises — no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _native as N
+from .plan import Plan
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def require_cuda():
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError("pgmpy_b200 needs a CUDA device (B200); there is no CPU execution path")
+    return torch
+
+
+class CompiledPlan:
+    """A Plan resident on one GPU. `dtype`: "float64" (default, 1e-12 parity target) or "float32"."""
+
+    def __init__(self, plan: Plan, dtype: str = "float64", device: Optional[int] = None):
+        torch = require_cuda()
+        self.lib = N.load()
+        self.plan = plan
+        self.dtype_name = dtype
+        self.torch_dtype = {"float64": torch.float64, "float32": torch.float32}[dtype]
+        self.pgx_dtype = N.PGX_F64 if dtype == "float64" else N.PGX_F32
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        with torch.cuda.device(self.device):
+            self.blob = torch.from_numpy(plan.const_blob).to(self.device, dtype=self.torch_dtype)
+            pool = np.ascontiguousarray(plan.pool, dtype=np.int32)
+            desc = N.PlanDesc(
+                1,
+                self.pgx_dtype,
+                pool.ctypes.data_as(C.POINTER(C.c_int32)),
+                pool.size,
+                C.c_void_p(self.blob.data_ptr()),
+                self.blob.numel(),
+            )
+            handle = C.c_void_p()
+            N.check(self.lib.pgx_plan_create(C.byref(desc), C.byref(handle)))
+        self.handle = handle
+        self.n_ev = len(plan.ev_vars)
+        self.out_elems = plan.out_elems
+        self._ws = None
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                self.lib.pgx_plan_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    # ---- options / info ----------------------------------------------------------------------
+    def set_mode(self, mode: str = "auto", fused_warps: int = 0):
+        m = {"auto": N.MODE_AUTO, "stepwise": N.MODE_STEPWISE, "fused": N.MODE_FUSED}[mode]
+        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_MODE, m))
+        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_FUSED_WARPS, fused_warps))
+
+    def info(self, what: int) -> int:
+        v = C.c_int64()
+        N.check(self.lib.pgx_plan_get_info(self.handle, what, C.byref(v)))
+        return v.value
+
+    @property
+    def last_launches(self) -> int:
+        return self.info(N.INFO_LAST_LAUNCHES)
+
+    @property
+    def last_mode(self) -> str:
+        return {N.MODE_STEPWISE: "stepwise", N.MODE_FUSED: "fused", 0: "none"}[self.info(N.INFO_LAST_MODE)]
+
+    def workspace_bytes(self, batch: int) -> int:
+        return int(self.lib.pgx_workspace_bytes(self.handle, batch))
+
+    # ---- execution ---------------------------------------------------------------------------
+    def run(self, ev_states, out=None, workspace=None):
+        """ev_states: int32 CUDA tensor [B, n_ev] (or [B, 0] / None with B given by `out`).
+        Returns out: [B, out_elems] CUDA tensor of the plan dtype. Asynchronous on the current stream."""
+        torch = _torch()
+        if ev_states is None:
+            if out is None:
+                raise ValueError("batch size unknown: pass ev_states or out")
+            B = out.shape[0]
+        else:
+            if ev_states.dtype != torch.int32 or not ev_states.is_cuda or not ev_states.is_contiguous():
+                raise ValueError("ev_states must be a contiguous int32 CUDA tensor")
+            if ev_states.dim() != 2 or ev_states.shape[1] != self.n_ev:
+                raise ValueError(f"ev_states must be [B, {self.n_ev}]")
+            B = ev_states.shape[0]
+        if B <= 0:
+            raise ValueError("empty batch")
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty((B, self.out_elems), dtype=self.torch_dtype, device=self.device)
+            elif out.dtype != self.torch_dtype or not out.is_contiguous() or tuple(out.shape) != (B, self.out_elems):
+                raise ValueError("out has the wrong dtype/shape")
+            need = self.workspace_bytes(B)
+            if workspace is None:
+                if self._ws is None or self._ws.numel() < need:
+                    self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+                workspace = self._ws
+            elif workspace.numel() * workspace.element_size() < need:
+                raise ValueError(f"workspace too small: need {need} bytes")
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            N.check(
+                self.lib.pgx_run_batch(
+                    self.handle,
+                    C.c_void_p(ev_states.data_ptr() if (ev_states is not None and self.n_ev) else 0),
+                    C.c_void_p(out.data_ptr()),
+                    C.c_void_p(workspace.data_ptr()),
+                    workspace.numel() * workspace.element_size(),
+                    B,
+                    C.c_void_p(stream),
+                )
+            )
+        return out
+
+    def run_pinned(self, ev_pinned, out_pinned, ev_dev=None, out_dev=None):
+        """End-to-end call with HOST buffers: pinned int32 [B, n_ev] in, pinned [B, out_elems] out.
+        Copies H2D, runs the plan, copies D2H on the current stream and waits for the result."""
+        torch = _torch()
+        B = ev_pinned.shape[0]
+        with torch.cuda.device(self.device):
+            if ev_dev is None:
+                ev_dev = torch.empty((B, self.n_ev), dtype=torch.int32, device=self.device)
+            if out_dev is None:
+                out_dev = torch.empty((B, self.out_elems), dtype=self.torch_dtype, device=self.device)
+            ev_dev.copy_(ev_pinned, non_blocking=True)
+            self.run(ev_dev if self.n_ev else None, out=out_dev)
+            out_pinned.copy_(out_dev, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        return out_pinned
+
+    def run_host(self, ev_states_np: np.ndarray) -> np.ndarray:
+        """Convenience: host int array [B, n_ev] -> host posteriors [B, out_elems] (range-checks the states)."""
+        torch = _torch()
+        ev = np.ascontiguousarray(ev_states_np, dtype=np.int32).reshape(-1, self.n_ev)
+        cards = [self.plan.card[v] for v in self.plan.ev_vars]
+        for j, c in enumerate(cards):
+            col = ev[:, j]
+            if col.size and (col.min() < 0 or col.max() >= c):
+                raise ValueError(f"evidence state out of range for {self.plan.ev_vars[j]}")
+        dev = torch.from_numpy(ev).to(self.device)
+        if self.n_ev == 0:
+            out = torch.empty((ev.shape[0], self.out_elems), dtype=self.torch_dtype, device=self.device)
+            return self.run(None, out=out).cpu().numpy()
+        return self.run(dev).cpu().numpy()

@@ -21,7 +21,8 @@ Every step is the same operation, a fused product + sum-out over a batch of evid
 
 Word pool layout (int32 words; 64-bit values as lo,hi):
   header[16]: 0 magic 'PGX1' | 1 version | 2 n_ev | 3 n_steps | 4 n_segs | 5 out_elems | 6,7 ws_entries
-              | 8,9 const_entries | 10 step_index_off | 11 segs_off | 12 max_ops | 13 max_axes | 14,15 0
+              | 8,9 const_entries | 10 step_index_off | 11 segs_off | 12 max_ops | 13 max_axes | 14 ev_card_off | 15 0
+  ev_card[n_ev]: cardinality of each evidence slot (states are range-checked against it)
   step_index[n_steps]: word offset of each step record
   step record: 0 A (#out axes) | 1 S (#sum axes) | 2 K (#operands) | 3 flags (bit0 max-reduce, bit1 has divisor)
                | 4,5 out_size | 6,7 sum_size | 8,9 out work offset | 10 level | 11 0
@@ -383,15 +384,16 @@ class PlanBuilder:
         const_len = max(self._const_len, 1)
         header = [MAGIC, VERSION, len(self.ev_vars), n_steps, len(self.segments), out_elems]
         header += [*_lohi(ws_entries), *_lohi(const_len)]
-        step_index_off = HEADER_WORDS
+        ev_card_off = HEADER_WORDS
+        step_index_off = ev_card_off + len(self.ev_vars)
         pos = step_index_off + n_steps
         index = []
         for r in step_recs:
             index.append(pos)
             pos += len(r)
         segs_off = pos
-        header += [step_index_off, segs_off, max_ops, max_axes, 0, 0]
-        words = header + index
+        header += [step_index_off, segs_off, max_ops, max_axes, ev_card_off, 0]
+        words = header + [self.card[v] for v in self.ev_vars] + index
         for r in step_recs:
             words += r
         for s in self.segments:

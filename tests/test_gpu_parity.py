@@ -1,0 +1,273 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracle, the reference's golden posteriors and the
+reference's known answers. Run on the B200 box: pytest -m gpu."""
+import json
+import warnings
+
+import numpy as np
+import pytest
+
+import pgmpy_b200 as px
+from oracle import pgm_oracle as O
+from oracle.plan_exec import run_plan
+from pgmpy_b200.evidence import sample_evidence
+from pgmpy_b200.planner import JTStructure, compile_jt_plan, compile_ve_plan
+
+from helpers import (SIX_NODE_ANSWERS, SNOW_ANSWERS, SNOW_VIRTUAL_1, SNOW_VIRTUAL_2, golden_models, load_golden,
+                     rel_err, six_node_net, snow_net)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _engine():
+    from pgmpy_b200.engine import CompiledPlan
+
+    return CompiledPlan
+
+
+@pytest.mark.parametrize("name", ["asia", "alarm", "hepar2", "win95pts"])
+@pytest.mark.parametrize("mode", ["fused", "stepwise"])
+def test_jt_all_marginals_vs_oracle(torch_cuda, name, mode):
+    """Same seeded evidence through the CUDA kernels and the numpy plan interpreter; fp64, 1e-12 relative."""
+    m = px.get_example_model(name)
+    jt = JTStructure.from_model(m)
+    for B in (1, 5, 32, 257):
+        ev_vars, states = sample_evidence(m, B, 2 if name == "asia" else 5, seed=B)
+        for distribute in ("auto", "divide"):
+            plan = compile_jt_plan(jt, ev_vars, distribute=distribute)
+            cp = _engine()(plan)
+            cp.set_mode(mode, 3 if mode == "fused" else 0)
+            got = cp.run_host(states)
+            want = run_plan(plan.pool, plan.const_blob, states)
+            assert rel_err(got, want) <= 1e-12
+            assert cp.last_mode == mode
+
+
+@pytest.mark.parametrize("name", golden_models())
+def test_ve_query_batch_vs_reference_golden(torch_cuda, name):
+    """VariableElimination.query_batch vs posteriors of the unmodified reference (VE mode incl. pruning)."""
+    from pgmpy_b200.inference import VariableElimination
+
+    g = load_golden(name)
+    m = px.get_example_model(name)
+    ve = VariableElimination(m)
+    by_q = {}
+    for case, q, want in g["ve"]:
+        by_q.setdefault(q, []).append((case, want))
+    worst = 0.0
+    for q, items in list(by_q.items())[:40]:
+        out = ve.query_batch([q], g["ev_vars"], g["ev_states"]).cpu().numpy()
+        for case, want in items:
+            worst = max(worst, rel_err(out[case], want))
+    assert worst <= 1e-12, worst
+
+
+@pytest.mark.parametrize("name", [n for n in golden_models() if n not in ("sachs", "munin", "diabetes")])
+def test_bp_marginals_batch_vs_reference_golden(torch_cuda, name):
+    """BeliefPropagation.marginals_batch vs the unmodified reference's BeliefPropagation.query on our tree."""
+    from pgmpy_b200.inference import BeliefPropagation
+
+    g = load_golden(name)
+    m = px.get_example_model(name)
+    bp = BeliefPropagation(m)
+    cp = bp.marginals_plan(g["ev_vars"])
+    out = bp.marginals_batch(g["ev_vars"], g["ev_states"]).cpu().numpy()
+    col = {s.vars[0]: (s.out_offset, s.table.size) for s in cp.plan.segments}
+    worst = 0.0
+    for case, q, want in g["bp"]:
+        o, n = col[q]
+        worst = max(worst, rel_err(out[case, o : o + n], want))
+    # pathfinder: the reference's own BP output is 1.2e-12 off an extended-precision evaluation (see test_planner)
+    assert worst <= (5e-12 if name == "pathfinder" else 1e-12), worst
+
+
+@pytest.mark.parametrize("name", ["pathfinder", "munin", "diabetes"])
+def test_large_models_stepwise_vs_oracle(torch_cuda, name):
+    """HBM-resident clique tables: stepwise kernels vs the numpy interpreter on a small batch."""
+    m = px.get_example_model(name)
+    jt = JTStructure.from_model(m)
+    ev_vars, states = sample_evidence(m, 3, 8, seed=2)
+    plan = compile_jt_plan(jt, ev_vars)
+    cp = _engine()(plan)
+    cp.set_mode("stepwise")
+    got = cp.run_host(states)
+    want = run_plan(plan.pool, plan.const_blob, states)
+    assert np.isfinite(got).all()
+    assert rel_err(got, want) <= 1e-12
+
+
+def test_known_answers_ve_and_bp(torch_cuda):
+    from pgmpy_b200.inference import BeliefPropagation, VariableElimination
+
+    m = six_node_net()
+    for algo in (VariableElimination, BeliefPropagation):
+        infer = algo(m)
+        for variables, evidence, want in SIX_NODE_ANSWERS:
+            res = infer.query(variables, evidence=evidence, show_progress=False)
+            assert res.variables == variables
+            np.testing.assert_allclose(res.values, want, atol=1e-8)
+        # query twice gives the same answer and leaves the model untouched (test_query_multiple_times)
+        r1 = infer.query(["J"]).values
+        r2 = infer.query(["J"]).values
+        np.testing.assert_array_equal(r1, r2)
+    s = snow_net()
+    for algo in (VariableElimination, BeliefPropagation):
+        infer = algo(s)
+        for variables, evidence, want in SNOW_ANSWERS:
+            res = infer.query(variables, evidence=evidence)
+            np.testing.assert_allclose(res.values, want, atol=1e-6)
+            assert res.state_names[variables[0]] == s.states[variables[0]]
+        with pytest.raises(ValueError):
+            infer.query(variables=["Traffic"], evidence={"Traffic": "slow"})
+    with pytest.raises(ValueError, match="at least one variable"):
+        VariableElimination(s).query(variables=[], evidence={"Snow": "yes"})
+    with pytest.raises(KeyError):
+        VariableElimination(s).query(["Late"], evidence={"Traffic": "fast"})
+    with pytest.raises(ValueError):
+        VariableElimination(s).query(["Late"], evidence={"Nope": "x"})
+
+
+def test_virtual_evidence_known_answers(torch_cuda):
+    from pgmpy_b200 import DiscreteFactor, TabularCPD
+    from pgmpy_b200.inference import BeliefPropagation, VariableElimination
+
+    s = snow_net()
+    v_cpd = TabularCPD("Traffic", 2, [[0.3], [0.7]], state_names={"Traffic": ["normal", "slow"]})
+    v_fac = DiscreteFactor(["Traffic"], [2], [0.3, 0.7], state_names={"Traffic": ["normal", "slow"]})
+    v1 = TabularCPD("Risk", 2, [[0.7], [0.3]], state_names={"Risk": ["yes", "no"]})
+    for algo in (VariableElimination, BeliefPropagation):
+        for virt in (v_cpd, v_fac):
+            infer = algo(s)
+            for variables, want in SNOW_VIRTUAL_1:
+                np.testing.assert_allclose(infer.query(variables, virtual_evidence=[virt]).values, want, atol=1e-6)
+            for variables, want in SNOW_VIRTUAL_2:
+                np.testing.assert_allclose(infer.query(variables, virtual_evidence=[virt, v1]).values, want, atol=1e-6)
+
+
+def test_joint_false_and_bp_joint(torch_cuda):
+    from pgmpy_b200.inference import BeliefPropagation, VariableElimination
+
+    m = px.get_example_model("alarm")
+    net = O.Net(m)
+    ev = {"CVP": "LOW", "HISTORY": "TRUE"}
+    ve = VariableElimination(m)
+    res = ve.query(["HRBP", "PAP"], evidence=ev, joint=False)
+    for v in ("HRBP", "PAP"):
+        assert rel_err(res[v].values, O.ve_query(net, [v], ev).values) <= 1e-9  # per-variable pruning differs at 1e-8
+    joint = ve.query(["HRBP", "PAP"], evidence=ev)
+    assert rel_err(joint.values, O.ve_query(net, ["HRBP", "PAP"], ev).values) <= 1e-12
+    bpj = BeliefPropagation(m).query(["HRBP", "PAP"], evidence=ev)
+    assert rel_err(bpj.values, O.ve_query(net, ["HRBP", "PAP"], ev, prune_model=False).values) <= 1e-12
+
+
+def test_calibrate_beliefs_vs_oracle(torch_cuda):
+    """get_clique_beliefs / get_sepset_beliefs after calibrate(): calibrated, and equal to the exact
+    clique marginals of prod(all potentials) (what the reference converges to, ExactInference.py:854-895)."""
+    from pgmpy_b200.inference import BeliefPropagation
+
+    m = px.get_example_model("asia")
+    bp = BeliefPropagation(m)
+    bp.calibrate()
+    jt = bp._jt
+    joint = O.factor_product(*[O.Factor(c, p) for c, p in zip(jt.cliques, jt.potentials)])
+    for c, f in bp.get_clique_beliefs().items():
+        want = O.marginalize(joint, [v for v in joint.variables if v not in c])
+        assert rel_err(f.values, O.reorder(want, list(f.variables))) <= 1e-12
+    for key, f in bp.get_sepset_beliefs().items():
+        want = O.marginalize(joint, [v for v in joint.variables if v not in f.variables])
+        assert rel_err(f.values, O.reorder(want, list(f.variables))) <= 1e-12
+    assert len(bp.get_sepset_beliefs()) == len(jt.cliques) - 1
+
+
+def test_impossible_evidence_gives_nan(torch_cuda):
+    """P(e) = 0 -> 0/0 = NaN values and a RuntimeWarning, no exception (DiscreteFactor.py:530)."""
+    from pgmpy_b200.inference import VariableElimination
+
+    m = px.get_example_model("asia")
+    ve = VariableElimination(m)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        res = ve.query(["bronc"], evidence={"either": "no", "lung": "yes"})
+    assert np.isnan(res.values).all()
+    assert any(issubclass(x.category, RuntimeWarning) for x in w)
+
+
+def test_fp32_mode_within_1e5(torch_cuda):
+    m = px.get_example_model("alarm")
+    jt = JTStructure.from_model(m)
+    ev_vars, states = sample_evidence(m, 512, 5, seed=9)
+    plan = compile_jt_plan(jt, ev_vars)
+    want = run_plan(plan.pool, plan.const_blob, states)
+    for mode in ("fused", "stepwise"):
+        cp = _engine()(plan, dtype="float32")
+        cp.set_mode(mode)
+        got = cp.run_host(states)
+        assert got.dtype == np.float32
+        assert np.max(np.abs(got - want)) <= 1e-5
+
+
+def test_full_size_batch_properties(torch_cuda):
+    """BASELINE size (131072 evidence sets / GPU): size-independent properties — every marginal sums to 1,
+    duplicated evidence rows give bit-identical rows, batch order does not matter, and fused == stepwise."""
+    torch = torch_cuda
+    from pgmpy_b200.inference import BeliefPropagation
+
+    m = px.get_example_model("alarm")
+    bp = BeliefPropagation(m)
+    B = 131072
+    ev_vars, states = sample_evidence(m, B, 5, seed=1)
+    cp = bp.marginals_plan(ev_vars)
+    cp.set_mode("fused")
+    ev = torch.from_numpy(states).cuda()
+    out = cp.run(ev).clone()
+    for seg in cp.plan.segments:
+        s = out[:, seg.out_offset : seg.out_offset + seg.table.size].sum(dim=1)
+        assert float((s - 1).abs().max()) <= 1e-12
+    perm = torch.randperm(B, device="cuda")
+    out_p = cp.run(ev[perm].contiguous())
+    assert torch.equal(out_p, out[perm])
+    cp.set_mode("stepwise")
+    out_s = cp.run(ev)
+    assert torch.equal(out_s, out)
+    # spot-check 64 rows against the oracle interpreter
+    idx = np.linspace(0, B - 1, 64).astype(int)
+    want = run_plan(cp.plan.pool, cp.plan.const_blob, states[idx])
+    assert rel_err(out[idx].cpu().numpy(), want) <= 1e-12
+
+
+def test_standalone_gather_and_normalize(torch_cuda):
+    """K1 / K4 entry points: pgx_evidence_reduce == DiscreteFactor.reduce per evidence set, pgx_normalize."""
+    import ctypes as C
+
+    torch = torch_cuda
+    from pgmpy_b200 import _native as N
+
+    lib = N.load()
+    rng = np.random.default_rng(0)
+    table = rng.random((3, 4, 2, 5))
+    B = 77
+    ev = np.stack([rng.integers(0, 4, B), rng.integers(0, 5, B)], axis=1).astype(np.int32)  # axes 1 and 3 observed
+    ldb = lib.pgx_batch_ld(B)
+    t_dev = torch.from_numpy(table.reshape(-1)).cuda()
+    ev_dev = torch.from_numpy(ev).cuda()
+    dst = torch.zeros((6, ldb), dtype=torch.float64, device="cuda")
+    arr = lambda xs: (C.c_int32 * len(xs))(*xs)
+    N.check(lib.pgx_evidence_reduce(0, C.c_void_p(t_dev.data_ptr()), table.size, 2, arr([3, 2]), arr([40, 5]), 2,
+                                    arr([0, 1]), arr([10, 1]), arr([4, 5]), C.c_void_p(ev_dev.data_ptr()), 2,
+                                    C.c_void_p(dst.data_ptr()), B, ldb, None))
+    torch.cuda.synchronize()
+    got = dst.cpu().numpy()[:, :B]
+    for b in range(B):
+        want = O.reduce(O.Factor(["a", "b", "c", "d"], table), [("b", ev[b, 0]), ("d", ev[b, 1])]).values.reshape(-1)
+        np.testing.assert_array_equal(got[:, b], want)
+    out = torch.zeros((B, 6), dtype=torch.float64, device="cuda")
+    N.check(lib.pgx_normalize(0, C.c_void_p(dst.data_ptr()), 6, ldb, C.c_void_p(out.data_ptr()), 6, B, None))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), (got / got.sum(axis=0)).T, rtol=1e-15)

@@ -1,0 +1,187 @@
+"""Host logic: graph algorithms, junction trees, plan compilation; plans are evaluated with the numpy plan
+interpreter (oracle/plan_exec.py) and with the host build of the device element function (tests/hostsim)."""
+import numpy as np
+import pytest
+
+import pgmpy_b200 as px
+from oracle import pgm_oracle as O
+from oracle.plan_exec import parse, run_plan
+from pgmpy_b200 import graph as G
+from pgmpy_b200.evidence import sample_evidence
+from pgmpy_b200.plan import MAX_OPS
+from pgmpy_b200.planner import JTStructure, compile_jt_plan, compile_ve_plan, evidence_to_states
+
+from helpers import (SIX_NODE_ANSWERS, SNOW_ANSWERS, golden_models, hostsim_run, load_golden, rel_err, six_node_net,
+                     snow_net)
+
+ALL_MODELS = ["asia", "cancer", "sachs", "child", "alarm", "hepar2", "win95pts", "pathfinder", "munin", "diabetes"]
+# (cliques, sum clique entries, sum sepset entries) of a correct min-fill tree, SURVEY.md Appendix A
+JT_STATS = {"alarm": (27, 1038, 238), "hepar2": (58, 2617, 688), "win95pts": (50, 2684, 878)}
+
+
+@pytest.mark.parametrize("name", ALL_MODELS)
+def test_junction_tree_is_valid(name):
+    m = px.get_example_model(name)
+    jt = JTStructure.from_model(m)
+    assert G.check_running_intersection(jt.cliques, jt.edges)
+    assert set(v for c in jt.cliques for v in c) == set(m.nodes())
+    for cpd in m.get_cpds():  # family preservation
+        assert any(set(cpd.variables) <= set(c) for c in jt.cliques)
+    if name in JT_STATS:
+        size = lambda vs: int(np.prod([jt.card[v] for v in vs]))
+        seps = sum(size(set(jt.cliques[a]) & set(jt.cliques[b])) for a, b in jt.edges)
+        assert (len(jt.cliques), sum(size(c) for c in jt.cliques), seps) == JT_STATS[name]
+
+
+def test_pruning_matches_oracle_kept_set():
+    m = px.get_example_model("alarm")
+    net = O.Net(m)
+    rng = np.random.default_rng(3)
+    nodes = sorted(m.nodes())
+    parents = {n: m.get_parents(n) for n in nodes}
+    children = {n: m.get_children(n) for n in nodes}
+    for _ in range(40):
+        E = list(rng.choice(nodes, 5, replace=False))
+        q = [v for v in nodes if v not in E][int(rng.integers(0, 32))]
+        kept, _ = O.prune(net, [q], {v: 0 for v in E})
+        assert G.prune_nodes(parents, children, [q], E) == kept
+
+
+def test_known_answers_through_plans():
+    m = six_node_net()
+    for variables, evidence, want in SIX_NODE_ANSWERS:
+        plan = compile_ve_plan(m, variables, list(evidence))
+        es = evidence_to_states(m.states, plan.ev_vars, [evidence])
+        got = run_plan(plan.pool, plan.const_blob, es)[0]
+        np.testing.assert_allclose(got, np.asarray(want).reshape(-1), atol=1e-8)
+    m = snow_net()
+    for variables, evidence, want in SNOW_ANSWERS:
+        plan = compile_ve_plan(m, variables, list(evidence))
+        es = evidence_to_states(m.states, plan.ev_vars, [evidence])
+        np.testing.assert_allclose(run_plan(plan.pool, plan.const_blob, es)[0], want, atol=1e-6)
+        with pytest.raises(KeyError):
+            evidence_to_states(m.states, plan.ev_vars, [{"Traffic": "fast"}])
+
+
+@pytest.mark.parametrize("name", golden_models())
+def test_ve_plans_match_reference_golden(name):
+    g = load_golden(name)
+    m = px.get_example_model(name)
+    limit = {"munin": 8, "diabetes": 3}.get(name, 48)
+    worst = 0.0
+    for case, q, want in g["ve"][:limit]:
+        plan = compile_ve_plan(m, [q], g["ev_vars"])
+        got = run_plan(plan.pool, plan.const_blob, g["ev_states"][case : case + 1])[0]
+        worst = max(worst, rel_err(got, want))
+    assert worst <= 1e-12, worst
+
+
+@pytest.mark.parametrize("name", [n for n in golden_models() if n not in ("sachs", "munin", "diabetes")])
+@pytest.mark.parametrize("distribute", ["auto", "ss", "divide"])
+def test_jt_plans_match_reference_golden(name, distribute):
+    g = load_golden(name)
+    m = px.get_example_model(name)
+    jt = JTStructure.from_model(m)
+    plan = compile_jt_plan(jt, g["ev_vars"], distribute=distribute)
+    out = run_plan(plan.pool, plan.const_blob, g["ev_states"])
+    col = {s.vars[0]: (s.out_offset, s.table.size) for s in plan.segments}
+    worst = 0.0
+    for case, q, want in g["bp"]:
+        o, n = col[q]
+        worst = max(worst, rel_err(out[case, o : o + n], want))
+    if name == "pathfinder":
+        # The reference's own BeliefPropagation result is 1.2e-12 away from an extended-precision evaluation
+        # here (belief-update divisions + convergence judged by allclose(atol=1e-8)), so
+        # 1e-12 against it is not attainable; we bound the gap and pin our result to long double instead.
+        exact = run_plan(plan.pool, plan.const_blob, g["ev_states"], dtype=np.longdouble).astype(np.float64)
+        assert rel_err(out, exact) <= 1e-13
+        assert worst <= 5e-12, worst
+    else:
+        assert worst <= 1e-12, worst
+
+
+def test_jt_plan_munin_against_unpruned_oracle():
+    """No BP golden for munin (the reference cannot calibrate it in reasonable time): check the BP-mode closed
+    form (all factors, no pruning) with the oracle's elimination on a few variables."""
+    m = px.get_example_model("munin")
+    jt = JTStructure.from_model(m)
+    ev_vars, states = sample_evidence(m, 2, 8, seed=0)
+    plan = compile_jt_plan(jt, ev_vars)
+    out = run_plan(plan.pool, plan.const_blob, states)
+    net = O.Net(m)
+    segs = plan.segments[::211]
+    for case in range(2):
+        ev = {v: m.states[v][int(s)] for v, s in zip(ev_vars, states[case])}
+        for seg in segs:
+            want = O.ve_query(net, [seg.vars[0]], ev, prune_model=False).values
+            got = out[case, seg.out_offset : seg.out_offset + seg.table.size]
+            assert rel_err(got, want) <= 1e-11
+
+
+@pytest.mark.parametrize("name", ["asia", "alarm", "hepar2", "win95pts", "pathfinder"])
+def test_hostsim_element_function_matches_plan_interpreter(name):
+    """Same packed plan through the g++ build of pgx_step.cuh::contract_elem and through numpy."""
+    m = px.get_example_model(name)
+    jt = JTStructure.from_model(m)
+    k = 2 if name == "asia" else 5
+    ev_vars, states = sample_evidence(m, 37 if name != "pathfinder" else 3, k, seed=4)
+    for distribute in ("auto", "divide"):
+        plan = compile_jt_plan(jt, ev_vars, distribute=distribute)
+        want = run_plan(plan.pool, plan.const_blob, states)
+        got = hostsim_run(plan, states)
+        assert rel_err(got, want) <= 1e-13
+    free = [v for v in sorted(m.nodes()) if v not in ev_vars]
+    plan = compile_ve_plan(m, free[:2], ev_vars, joint=True)
+    assert rel_err(hostsim_run(plan, states), run_plan(plan.pool, plan.const_blob, states)) <= 1e-13
+    plan = compile_ve_plan(m, free[:3], ev_vars, joint=False)
+    assert rel_err(hostsim_run(plan, states), run_plan(plan.pool, plan.const_blob, states)) <= 1e-13
+
+
+def test_hostsim_fp32_within_tolerance():
+    m = px.get_example_model("alarm")
+    jt = JTStructure.from_model(m)
+    ev_vars, states = sample_evidence(m, 64, 5, seed=5)
+    plan = compile_jt_plan(jt, ev_vars)
+    want = run_plan(plan.pool, plan.const_blob, states)
+    got = hostsim_run(plan, states, dtype=np.float32)
+    assert np.max(np.abs(got - want)) <= 1e-5
+
+
+def test_wide_products_are_split():
+    """pathfinder's hub clique has 57 neighbours; no step may exceed MAX_OPS operands."""
+    m = px.get_example_model("pathfinder")
+    jt = JTStructure.from_model(m)
+    plan = compile_jt_plan(jt, [])
+    _, steps, _ = parse(plan.pool)
+    assert max(s["K"] for s in steps) <= MAX_OPS
+    assert max(len(nb) for nb in jt.nb) > MAX_OPS
+
+
+def test_workspace_liveness_no_overlap():
+    """A step's output never overlaps a table that is still live (checked by brute force on alarm)."""
+    m = px.get_example_model("alarm")
+    plan = compile_jt_plan(JTStructure.from_model(m), ["CVP", "HR"])
+    live_until = {}
+    for i, st in enumerate(plan.steps):
+        for t, _ in st.operands:
+            if t.kind == 1:
+                live_until[t.tid] = i
+    for s in plan.segments:
+        live_until[s.table.tid] = len(plan.steps)
+    born = {st.out.tid: (i, st.out) for i, st in enumerate(plan.steps)}
+    for tid, (i, t) in born.items():
+        for tid2, (j, t2) in born.items():
+            if tid2 == tid or j >= i:
+                continue
+            if live_until.get(tid2, j) >= i:  # t2 still live when t is written
+                assert t.offset + t.size <= t2.offset or t2.offset + t2.size <= t.offset
+
+
+def test_evidence_sampler_is_deterministic_and_possible():
+    m = px.get_example_model("pathfinder")
+    ev1, s1 = sample_evidence(m, 16, 8, seed=0)
+    ev2, s2 = sample_evidence(m, 16, 8, seed=0)
+    assert ev1 == ev2 and np.array_equal(s1, s2)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev1)
+    out = run_plan(plan.pool, plan.const_blob, s1)
+    assert np.isfinite(out).all()  # forward-sampled evidence always has P(e) > 0
