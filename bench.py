@@ -32,8 +32,8 @@ UNIT = "evidence-queries/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="alarm")
     ap.add_argument("--batch-per-gpu", type=int, default=131072)
@@ -77,7 +77,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
             self.thread = threading.Thread(target=self._pump, daemon=True)
@@ -89,7 +89,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, first=0):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -99,7 +99,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[first:]:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 6:
                 continue
@@ -284,12 +284,20 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") -------------------------------------------------
-    for i in range(args.warmup):
-        cp.run(ev_dev[i % n_batches], out=out_dev)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        cp.run(ev_dev[i % n_batches], out=out_dev)
+    barrier()
+    if rank == 0:
+        # keep the GPU busy (untimed) until nvidia-smi has produced its first samples
+        t_wait = time.perf_counter()
+        while len(sampler.lines) < 2 and time.perf_counter() - t_wait < 3.0:
+            cp.run(ev_dev[0], out=out_dev)
+            torch.cuda.synchronize()
+    barrier()
+    n_before = len(sampler.lines)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall = time.perf_counter()
@@ -302,7 +310,13 @@ def run_b200(args):
     dev_ms = start.elapsed_time(stop)
     launches = cp.last_launches * args.steps
     mode = cp.last_mode
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0 and len(sampler.lines) - n_before < 2:
+        # very short timed region: take a few more samples under the same load (untimed)
+        t_wait = time.perf_counter()
+        while len(sampler.lines) - n_before < 3 and time.perf_counter() - t_wait < 2.0:
+            cp.run(ev_dev[0], out=out_dev)
+            torch.cuda.synchronize()
+    clocks = sampler.stop(n_before) if rank == 0 else None
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -149,14 +149,15 @@ class CompiledPlan:
     def run_host(self, ev_states_np: np.ndarray) -> np.ndarray:
         """Convenience: host int array [B, n_ev] -> host posteriors [B, out_elems] (range-checks the states)."""
         torch = _torch()
-        ev = np.ascontiguousarray(ev_states_np, dtype=np.int32).reshape(-1, self.n_ev)
+        ev = np.ascontiguousarray(ev_states_np, dtype=np.int32).reshape(-1, max(self.n_ev, 1))
         cards = [self.plan.card[v] for v in self.plan.ev_vars]
         for j, c in enumerate(cards):
             col = ev[:, j]
             if col.size and (col.min() < 0 or col.max() >= c):
                 raise ValueError(f"evidence state out of range for {self.plan.ev_vars[j]}")
-        dev = torch.from_numpy(ev).to(self.device)
         if self.n_ev == 0:
-            out = torch.empty((ev.shape[0], self.out_elems), dtype=self.torch_dtype, device=self.device)
+            B = max(1, int(np.asarray(ev_states_np).shape[0])) if np.asarray(ev_states_np).ndim >= 1 else 1
+            out = torch.empty((B, self.out_elems), dtype=self.torch_dtype, device=self.device)
             return self.run(None, out=out).cpu().numpy()
+        dev = torch.from_numpy(ev).to(self.device)
         return self.run(dev).cpu().numpy()

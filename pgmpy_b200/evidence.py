@@ -56,11 +56,14 @@ def forward_sample(model, n: int, rng: np.random.Generator) -> Tuple[List[Hashab
 
 def sample_evidence(model, batch: int, k: int, seed: int = 0, evidence_vars: Sequence[Hashable] = None):
     """(evidence_vars, states int32 [batch, k]) for one batch with a common observed set."""
+    nodes = list(model.nodes())
+    if evidence_vars is None:
+        # the observed set depends on (seed, k) only, not on the batch size
+        names = sorted(nodes, key=str)
+        pick = np.random.default_rng([seed, 0x0E]).choice(len(names), size=k, replace=False)
+        evidence_vars = [names[i] for i in pick]
     rng = np.random.default_rng(seed)
     nodes, samples = forward_sample(model, batch, rng)
-    if evidence_vars is None:
-        names = sorted(nodes, key=str)
-        evidence_vars = [names[i] for i in rng.choice(len(names), size=k, replace=False)]
     col = {v: i for i, v in enumerate(nodes)}
     states = np.ascontiguousarray(samples[:, [col[v] for v in evidence_vars]], dtype=np.int32)
     return list(evidence_vars), states

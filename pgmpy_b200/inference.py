@@ -87,6 +87,10 @@ class _Inference:
 
     def _run(self, cp: CompiledPlan, ev_states):
         torch = require_cuda()
+        if cp.n_ev == 0:
+            B = int(ev_states.shape[0]) if ev_states is not None and hasattr(ev_states, "shape") else 1
+            out = torch.empty((max(B, 1), cp.out_elems), dtype=cp.torch_dtype, device=cp.device)
+            return cp.run(None, out=out)
         if isinstance(ev_states, np.ndarray) or not hasattr(ev_states, "is_cuda"):
             ev = np.ascontiguousarray(np.asarray(ev_states, dtype=np.int32)).reshape(-1, cp.n_ev)
             for j, v in enumerate(cp.plan.ev_vars):
@@ -95,10 +99,6 @@ class _Inference:
             ev_t = torch.from_numpy(ev).to(cp.device)
         else:
             ev_t = ev_states
-        if cp.n_ev == 0:
-            B = ev_t.shape[0] if ev_t is not None else 1
-            out = torch.empty((B, cp.out_elems), dtype=cp.torch_dtype, device=cp.device)
-            return cp.run(None, out=out)
         return cp.run(ev_t)
 
     @staticmethod
