@@ -1,0 +1,50 @@
+"""Multi-GPU plumbing: one process per GPU, evidence sets sharded across ranks, no collective on the
+inference path; the only collective is the final posterior gather (NCCL all-gather over NVLink on GPUs,
+gloo in the CPU tests). Evidence sets never interact, so plans and tables are replicated."""
+from __future__ import annotations
+
+from typing import Tuple
+
+
+def shard_range(n: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of `n` evidence sets for `rank`; sizes differ by at most one."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank out of range")
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_rows(x, world_size: int, rank: int):
+    lo, hi = shard_range(x.shape[0], world_size, rank)
+    return x[lo:hi]
+
+
+def gather_posteriors(local, total_rows: int = None, group=None):
+    """All-gather the per-rank posterior rows [B_r, out_elems] into [sum B_r, out_elems] on every rank,
+    in rank order (ragged shards are padded to the largest shard for the collective and trimmed after)."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    rows = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    all_rows = [torch.zeros_like(rows) for _ in range(world)]
+    dist.all_gather(all_rows, rows, group=group)
+    counts = [int(r.item()) for r in all_rows]
+    width = local.shape[1]
+    biggest = max(counts)
+    padded = local
+    if local.shape[0] != biggest:
+        padded = torch.zeros((biggest, width), dtype=local.dtype, device=local.device)
+        padded[: local.shape[0]] = local
+    full = torch.empty((world * biggest, width), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(full, padded.contiguous(), group=group)
+    if all(c == biggest for c in counts):
+        out = full
+    else:
+        out = torch.cat([full[r * biggest : r * biggest + counts[r]] for r in range(world)], dim=0)
+    if total_rows is not None and out.shape[0] != total_rows:
+        raise RuntimeError("gathered row count does not match the batch")
+    return out
