@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
     ap.add_argument("--mode", default="auto", choices=["auto", "fused", "stepwise"])
     ap.add_argument("--fused-warps", type=int, default=0)
+    ap.add_argument("--fused-kernel", default="auto", choices=["auto", "generic", "tables-smem", "tables-global"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -268,7 +269,7 @@ def run_b200(args):
     # same evidence-variable set on every rank; each rank draws its own shard of evidence sets
     ev_vars, _ = sample_evidence(model, 1, k, seed=1)
     cp = bp.marginals_plan(ev_vars)
-    cp.set_mode(args.mode, args.fused_warps)
+    cp.set_mode(args.mode, args.fused_warps, args.fused_kernel)
     n_batches = 2
     shards = []
     for j in range(n_batches):
@@ -310,6 +311,7 @@ def run_b200(args):
     dev_ms = start.elapsed_time(stop)
     launches = cp.last_launches * args.steps
     mode = cp.last_mode
+    variant = cp.last_variant
     if rank == 0 and len(sampler.lines) - n_before < 2:
         # very short timed region: take a few more samples under the same load (untimed)
         t_wait = time.perf_counter()
@@ -377,7 +379,8 @@ def run_b200(args):
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
         roofline = {
             "bound": "hbm",
-            "kernel": "k_plan_fused" if mode == "fused" else "k_contract_step (sum over the step sequence)",
+            "kernel": {"generic": "k_plan_fused", "tables-smem": "k_plan_fused2<smem>", "tables-global": "k_plan_fused2<global>"}.get(
+                variant, "k_contract_step (sum over the step sequence)"),
             "achieved": achieved,
             "peak": peak,
             "unit": "GB/s",
@@ -408,7 +411,7 @@ def run_b200(args):
             "vs_baseline": None,
             "dtype": "f64" if args.dtype == "float64" else "f32",
             "data": "synthetic",
-            "config": dict(cfg, exec_mode=mode, l2="per-step working set (workspace %.0f MB + posteriors %.0f MB) exceeds the 126 MB L2; two evidence batches alternate"
+            "config": dict(cfg, exec_mode=mode, kernel_variant=variant, distribute=cp.plan.meta.get("distribute"), l2="per-step working set (workspace %.0f MB + posteriors %.0f MB) exceeds the 126 MB L2; two evidence batches alternate"
                            % (cp.workspace_bytes(B) / 1e6, B * cp.out_elems * itemsize / 1e6)),
             "marginals_per_sec": value * len(cp.plan.segments),
             "roofline": roofline,

@@ -59,6 +59,8 @@ extern "C" {
 #define PGX_OPT_MODE 1
 #define PGX_OPT_FUSED_WARPS 2 /* warps cooperating on one row of 32 evidence sets in fused mode (1..32) */
 #define PGX_OPT_USE_GRAPH 3   /* stepwise mode: replay the launch sequence as a CUDA graph (0/1) */
+#define PGX_OPT_FUSED_KERNEL 4 /* 0 auto | 1 generic addressing | 2 offset tables + shared-memory work tables |
+                                  3 offset tables + global work tables */
 
 #define PGX_INFO_N_STEPS 1
 #define PGX_INFO_OUT_ELEMS 2
@@ -66,6 +68,8 @@ extern "C" {
 #define PGX_INFO_LAST_LAUNCHES 4 /* kernels launched by the most recent pgx_run_batch */
 #define PGX_INFO_LAST_MODE 5
 #define PGX_INFO_N_EV 6
+#define PGX_INFO_LAST_VARIANT 7 /* which fused kernel ran (PGX_OPT_FUSED_KERNEL numbering), 0 if stepwise */
+#define PGX_INFO_N_LEVELS 8     /* dependency levels of the plan (0 when no offset tables were built) */
 
 typedef struct pgx_plan pgx_plan; /* opaque */
 

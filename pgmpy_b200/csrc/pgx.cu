@@ -22,6 +22,7 @@
 
 #include "../../include/pgx.h"
 #include "pgx_step.cuh"
+#include "pgx_fused.cuh"
 
 namespace {
 
@@ -186,9 +187,14 @@ struct pgx_plan {
     int32_t* d_pool = nullptr;
     const void* blob = nullptr;
     int64_t max_joint = 0;  // max over steps of out_size * sum_size
+    // table-driven fused kernel (pgx_fused.cuh)
+    pgx::MicroInfo micro;
+    int32_t* d_micro = nullptr;
     // options
     int mode = PGX_MODE_AUTO;
     int fused_warps = 0;  // 0 = auto
+    int fused_kernel = 0; // 0 = auto, 1 = generic (v1), 2 = table-driven/shared workspace, 3 = table-driven/global workspace
+    int last_variant = 0;
     // info
     int64_t last_launches = 0;
     int last_mode = 0;
@@ -322,6 +328,8 @@ int pgx_plan_create(const pgx_plan_desc* desc, pgx_plan** out) {
     }
     (void)out_total;
     pl->pool.assign(p, p + W);
+    std::vector<int32_t> micro_words;
+    if (pl->n_steps > 0 && pl->max_joint <= (1 << 16)) build_micro(p, micro_words, pl->micro);
     cudaError_t e = cudaGetDevice(&pl->device);
     if (e != cudaSuccess) return bad(PGX_ERR_CUDA, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
     e = cudaMalloc((void**)&pl->d_pool, (size_t)W * sizeof(int32_t));
@@ -331,6 +339,16 @@ int pgx_plan_create(const pgx_plan_desc* desc, pgx_plan** out) {
         cudaFree(pl->d_pool);
         return bad(PGX_ERR_CUDA, std::string("cudaMemcpy(pool): ") + cudaGetErrorString(e));
     }
+    if (pl->micro.ok) {
+        e = cudaMalloc((void**)&pl->d_micro, micro_words.size() * sizeof(int32_t));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(pl->d_micro, micro_words.data(), micro_words.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(pl->d_pool);
+            if (pl->d_micro) cudaFree(pl->d_micro);
+            return bad(PGX_ERR_CUDA, std::string("microprogram upload: ") + cudaGetErrorString(e));
+        }
+    }
     *out = pl;
     return PGX_OK;
 }
@@ -338,6 +356,7 @@ int pgx_plan_create(const pgx_plan_desc* desc, pgx_plan** out) {
 void pgx_plan_destroy(pgx_plan* plan) {
     if (!plan) return;
     if (plan->d_pool) cudaFree(plan->d_pool);
+    if (plan->d_micro) cudaFree(plan->d_micro);
     delete plan;
 }
 
@@ -355,8 +374,12 @@ int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
             plan->mode = (int)value;
             return PGX_OK;
         case PGX_OPT_FUSED_WARPS:
-            if (value < 0 || value > 32) return fail(PGX_ERR_INVALID, "fused warps must be 0..32");
+            if (value < 0 || value > 16) return fail(PGX_ERR_INVALID, "fused warps must be 0..16");
             plan->fused_warps = (int)value;
+            return PGX_OK;
+        case PGX_OPT_FUSED_KERNEL:
+            if (value < 0 || value > 3) return fail(PGX_ERR_INVALID, "fused kernel must be 0..3");
+            plan->fused_kernel = (int)value;
             return PGX_OK;
         default:
             return fail(PGX_ERR_UNSUPPORTED, "unknown option");
@@ -372,6 +395,8 @@ int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value) {
         case PGX_INFO_LAST_LAUNCHES: *value = plan->last_launches; break;
         case PGX_INFO_LAST_MODE: *value = plan->last_mode; break;
         case PGX_INFO_N_EV: *value = plan->n_ev; break;
+        case PGX_INFO_LAST_VARIANT: *value = plan->last_variant; break;
+        case PGX_INFO_N_LEVELS: *value = plan->micro.ok ? plan->micro.n_levels : 0; break;
         default: return fail(PGX_ERR_UNSUPPORTED, "unknown info key");
     }
     return PGX_OK;
@@ -390,7 +415,39 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
     int mode = pl->mode;
     if (mode == PGX_MODE_AUTO) mode = (pl->max_joint <= 8192 && B >= 2048) ? PGX_MODE_FUSED : PGX_MODE_STEPWISE;
     int64_t launches = 0;
-    if (mode == PGX_MODE_FUSED) {
+    if (mode == PGX_MODE_FUSED && pl->micro.ok && pl->fused_kernel != 1) {
+        // table-driven kernel; work tables in shared memory when a row of 32 evidence sets fits
+        const int64_t rows = (B + 31) / 32;
+        const size_t ws_smem = (size_t)pl->ws_entries * 32 * sizeof(T);
+        const size_t ev_smem = (size_t)pl->n_ev * 32 * sizeof(int32_t);
+        const size_t limit = 227 * 1024 - 1024;
+        const bool smem = ws_smem + ev_smem <= limit && pl->fused_kernel != 3;
+        const size_t dyn = (smem ? ws_smem : 0) + ev_smem;
+        int G = pl->fused_warps;
+        if (G <= 0) {
+            if (smem) {
+                const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (228 * 1024) / (dyn + 1024)));
+                G = (24 + per_sm - 1) / per_sm;  // ~24 warps per SM
+                if (G < 4) G = 4;
+            } else {
+                G = (int)((148 * 16 + rows - 1) / rows);
+            }
+        }
+        if (G < 1) G = 1;
+        if (G > 16) G = 16;
+        if (smem) {
+            PGX_CUDA(cudaFuncSetAttribute(k_plan_fused2<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            k_plan_fused2<T, true><<<(unsigned)rows, 32 * G, dyn, st>>>(pl->d_micro, cst, ws, ev, pl->d_pool + pl->ev_card_off,
+                                                                      out, pl->n_ev, (int)pl->ws_entries, B, ldb);
+        } else {
+            k_plan_fused2<T, false><<<(unsigned)rows, 32 * G, dyn, st>>>(pl->d_micro, cst, ws, ev, pl->d_pool + pl->ev_card_off,
+                                                                       out, pl->n_ev, (int)pl->ws_entries, B, ldb);
+        }
+        PGX_CUDA(cudaGetLastError());
+        launches = 1;
+        pl->last_variant = smem ? 2 : 3;
+    } else if (mode == PGX_MODE_FUSED) {
+        pl->last_variant = 1;
         int G = pl->fused_warps;
         const int64_t rows = (B + 31) / 32;
         if (G <= 0) {
@@ -442,6 +499,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
             ++launches;
         }
     }
+    if (mode != PGX_MODE_FUSED) pl->last_variant = 0;
     pl->last_launches = launches;
     pl->last_mode = mode;
     return PGX_OK;

@@ -66,10 +66,12 @@ class CompiledPlan:
             self.handle = None
 
     # ---- options / info ----------------------------------------------------------------------
-    def set_mode(self, mode: str = "auto", fused_warps: int = 0):
+    def set_mode(self, mode: str = "auto", fused_warps: int = 0, fused_kernel: str = "auto"):
+        """mode: auto | stepwise | fused.  fused_kernel: auto | generic | tables-smem | tables-global."""
         m = {"auto": N.MODE_AUTO, "stepwise": N.MODE_STEPWISE, "fused": N.MODE_FUSED}[mode]
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_MODE, m))
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_FUSED_WARPS, fused_warps))
+        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_FUSED_KERNEL, N.FUSED_KERNELS[fused_kernel]))
 
     def info(self, what: int) -> int:
         v = C.c_int64()
@@ -83,6 +85,11 @@ class CompiledPlan:
     @property
     def last_mode(self) -> str:
         return {N.MODE_STEPWISE: "stepwise", N.MODE_FUSED: "fused", 0: "none"}[self.info(N.INFO_LAST_MODE)]
+
+    @property
+    def last_variant(self) -> str:
+        v = self.info(N.INFO_LAST_VARIANT)
+        return {0: "stepwise", 1: "generic", 2: "tables-smem", 3: "tables-global"}[v]
 
     def workspace_bytes(self, batch: int) -> int:
         return int(self.lib.pgx_workspace_bytes(self.handle, batch))

@@ -132,6 +132,16 @@ class Plan:
         total += 4 * batch * len(self.ev_vars) + itemsize * batch * self.out_elems
         return total
 
+    def operand_loads(self) -> int:
+        """Operand loads (= multiplies) per evidence set: sum over steps of |out| * |sum| * #operands."""
+        total = 0
+        for st in self.steps:
+            joint = st.out.size
+            for v in st.sum_vars:
+                joint *= self.card[v]
+            total += joint * max(1, len(st.operands))
+        return total
+
     def flops(self, batch: int) -> int:
         f = 0
         for st in self.steps:
@@ -321,17 +331,40 @@ class PlanBuilder:
         return rec
 
     def finalize(self, meta: Optional[dict] = None) -> Plan:
-        # liveness-based first-fit allocation of work tables (steps run in order on one stream)
+        # 1. dependency levels (longest path): a step's level is one more than the deepest producer of its
+        #    work operands. Steps of one level are mutually independent, so the fused kernel may run them
+        #    concurrently; sorting by level keeps the sequential order valid for the stepwise path.
+        producer = {st.out.tid: i for i, st in enumerate(self.steps)}
+        level = [0] * len(self.steps)
+        for i, st in enumerate(self.steps):
+            lv = 0
+            for t, _ in st.operands:
+                if t.kind == KIND_WORK:
+                    lv = max(lv, level[producer[t.tid]] + 1)
+            level[i] = lv
+            st.level = lv
+        order = sorted(range(len(self.steps)), key=lambda i: (level[i], i))
+        self.steps = [self.steps[i] for i in order]
         n_steps = len(self.steps)
+        # 2. liveness in units of levels: a table is born at its producer's level and dies after the last
+        #    level that reads it (emitted tables never die)
+        for t in self.tables:
+            t.first_step = -1
+            if t.last_step < (1 << 59):
+                t.last_step = -1
+        for st in self.steps:
+            st.out.first_step = st.level
+            for t, _ in st.operands:
+                if t.kind == KIND_WORK and t.last_step < (1 << 59):
+                    t.last_step = max(t.last_step, st.level)
         work = [t for t in self.tables if t.kind == KIND_WORK and t.first_step >= 0]
         for t in work:
             if t.last_step < 0:
                 t.last_step = t.first_step
-        by_birth = sorted(work, key=lambda t: t.first_step)
+        by_birth = sorted(work, key=lambda t: (t.first_step, t.tid))
         free: List[Tuple[int, int]] = []  # (offset, size), kept sorted by offset
         live: List[Table] = []
         top = 0
-        ALIGN = 1
 
         def release(t):
             nonlocal free
@@ -346,8 +379,7 @@ class PlanBuilder:
             free = merged
 
         for t in by_birth:
-            # a step may not write a table overlapping one of its own operands: free only tables whose
-            # last use is strictly before this step
+            # memory is recycled only from tables whose last reader ran in a strictly earlier level
             still = []
             for l in live:
                 if l.last_step < t.first_step:
@@ -357,15 +389,18 @@ class PlanBuilder:
             live = still
             need = max(1, t.size)
             placed = False
-            for i, (off, sz) in enumerate(free):
-                if sz >= need:
-                    t.offset = off
-                    if sz == need:
-                        free.pop(i)
-                    else:
-                        free[i] = (off + need, sz - need)
-                    placed = True
-                    break
+            best = None
+            for i, (off, sz) in enumerate(free):  # best fit
+                if sz >= need and (best is None or sz < free[best][1]):
+                    best = i
+            if best is not None:
+                off, sz = free[best]
+                t.offset = off
+                if sz == need:
+                    free.pop(best)
+                else:
+                    free[best] = (off + need, sz - need)
+                placed = True
             if not placed:
                 if free and free[-1][0] + free[-1][1] == top:
                     off, sz = free.pop()

@@ -360,6 +360,12 @@ def compile_jt_plan(
     `variables=None` means every unobserved variable of the tree (all-marginals query).
     `emit_beliefs=True` emits the calibrated clique beliefs and sepset beliefs instead (un-normalised,
     like get_clique_beliefs/get_sepset_beliefs, :750-768)."""
+    if distribute == "auto" and not emit_beliefs:
+        # Shafer-Shenoy keeps the workspace smallest (messages only: fits shared memory for alarm-class models);
+        # belief-update wins when high-degree cliques would recompute their product once per neighbour.
+        cands = [compile_jt_plan(jt, evidence_vars, variables, normalize, False, d) for d in ("ss", "belief")]
+        cost = [p.operand_loads() for p in cands]
+        return cands[0] if cost[0] <= 1.2 * cost[1] else cands[1]
     ev = list(evidence_vars)
     evset = set(ev)
     card = jt.card
@@ -403,7 +409,7 @@ def compile_jt_plan(
             return False
         if distribute == "divide":
             return len(jt.children[i]) >= 1
-        return len(jt.nb[i]) >= 3 and len(jt.children[i]) >= 2
+        return len(jt.nb[i]) >= 3 and len(jt.children[i]) >= 2  # "belief" (and "auto" when it resolves to it)
 
     for i in jt.pre:
         lvl = base_level + 2 * jt.depth[i]
@@ -465,7 +471,8 @@ def compile_jt_plan(
             t = b.contract([psi[i]] + incoming(i), [v], level=final_level)
         b.emit(t, normalize, [v])
     return b.finalize(
-        {"mode": "jt", "evidence_vars": tuple(ev), "variables": tuple(variables), "root": jt.root, "n_cliques": n}
+        {"mode": "jt", "evidence_vars": tuple(ev), "variables": tuple(variables), "root": jt.root, "n_cliques": n,
+         "distribute": distribute}
     )
 
 

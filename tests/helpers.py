@@ -124,3 +124,23 @@ def bp_reference_tolerance(want, exact):
     evaluation of the same closed form, on alarm 2e-15. Where the reference is itself within 1e-12 of the
     exact value we demand 1e-12; elsewhere we allow twice the reference's own residual."""
     return max(1e-12, 2.0 * rel_err(want, exact))
+
+
+def hostsim_micro_run(plan, ev):
+    """Walks the table-driven microprogram (pgx_fused.cuh::build_micro) on the CPU. Returns (out, n_levels)."""
+    global _hostsim
+    if _hostsim is None:
+        _hostsim = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "_hostsim.so"))
+    ev = np.ascontiguousarray(np.asarray(ev, dtype=np.int32)).reshape(-1, max(1, len(plan.ev_vars)))
+    B = ev.shape[0]
+    ldb = (B + 31) // 32 * 32 if B >= 32 else 1 << max(0, (B - 1).bit_length())
+    pool = np.ascontiguousarray(plan.pool)
+    cst = np.ascontiguousarray(plan.const_blob)
+    ws = np.zeros(plan.ws_entries * ldb)
+    out = np.zeros((B, plan.out_elems))
+    nl = C.c_int32(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = _hostsim.hostsim_micro_f64(p(pool), p(cst), p(ev), p(ws), p(out), C.c_int64(B), C.c_int64(ldb), C.byref(nl))
+    if rc != 0:
+        raise RuntimeError("plan too large for a microprogram")
+    return out, nl.value

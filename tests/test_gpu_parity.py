@@ -32,22 +32,40 @@ def _engine():
     return CompiledPlan
 
 
+EXEC_VARIANTS = [("stepwise", "auto"), ("fused", "generic"), ("fused", "tables-smem"), ("fused", "tables-global")]
+
+
 @pytest.mark.parametrize("name", ["asia", "alarm", "hepar2", "win95pts"])
-@pytest.mark.parametrize("mode", ["fused", "stepwise"])
-def test_jt_all_marginals_vs_oracle(torch_cuda, name, mode):
-    """Same seeded evidence through the CUDA kernels and the numpy plan interpreter; fp64, 1e-12 relative."""
+@pytest.mark.parametrize("mode,kernel", EXEC_VARIANTS)
+def test_jt_all_marginals_vs_oracle(torch_cuda, name, mode, kernel):
+    """Same seeded evidence through every CUDA execution variant and the numpy plan interpreter; fp64, 1e-12."""
     m = px.get_example_model(name)
     jt = JTStructure.from_model(m)
     for B in (1, 5, 32, 257):
         ev_vars, states = sample_evidence(m, B, 2 if name == "asia" else 5, seed=B)
-        for distribute in ("auto", "divide"):
+        for distribute in ("ss", "belief", "divide"):
             plan = compile_jt_plan(jt, ev_vars, distribute=distribute)
             cp = _engine()(plan)
-            cp.set_mode(mode, 3 if mode == "fused" else 0)
+            cp.set_mode(mode, 3 if mode == "fused" else 0, kernel)
             got = cp.run_host(states)
             want = run_plan(plan.pool, plan.const_blob, states)
             assert rel_err(got, want) <= 1e-12
             assert cp.last_mode == mode
+            if mode == "fused" and kernel == "tables-global":
+                assert cp.last_variant == "tables-global"
+            if mode == "fused" and kernel == "generic":
+                assert cp.last_variant == "generic"
+
+
+def test_shared_memory_variant_is_selected_for_alarm(torch_cuda):
+    m = px.get_example_model("alarm")
+    ev_vars, states = sample_evidence(m, 4096, 5, seed=1)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars)
+    assert plan.meta["distribute"] == "ss"
+    cp = _engine()(plan)
+    got = cp.run_host(states)
+    assert (cp.last_mode, cp.last_variant) == ("fused", "tables-smem")
+    assert rel_err(got, run_plan(plan.pool, plan.const_blob, states)) <= 1e-12
 
 
 @pytest.mark.parametrize("name", golden_models())
@@ -213,9 +231,9 @@ def test_fp32_mode_within_1e5(torch_cuda):
     ev_vars, states = sample_evidence(m, 512, 5, seed=9)
     plan = compile_jt_plan(jt, ev_vars)
     want = run_plan(plan.pool, plan.const_blob, states)
-    for mode in ("fused", "stepwise"):
+    for mode, kernel in EXEC_VARIANTS:
         cp = _engine()(plan, dtype="float32")
-        cp.set_mode(mode)
+        cp.set_mode(mode, 0, kernel)
         got = cp.run_host(states)
         assert got.dtype == np.float32
         assert np.max(np.abs(got - want)) <= 1e-5
@@ -235,6 +253,10 @@ def test_full_size_batch_properties(torch_cuda):
     cp.set_mode("fused")
     ev = torch.from_numpy(states).cuda()
     out = cp.run(ev).clone()
+    assert cp.last_variant == "tables-smem"
+    cp.set_mode("fused", 0, "generic")
+    assert torch.equal(cp.run(ev), out)
+    cp.set_mode("fused")
     for seg in cp.plan.segments:
         s = out[:, seg.out_offset : seg.out_offset + seg.table.size].sum(dim=1)
         assert float((s - 1).abs().max()) <= 1e-12

@@ -11,7 +11,7 @@ from pgmpy_b200.evidence import sample_evidence
 from pgmpy_b200.plan import MAX_OPS
 from pgmpy_b200.planner import JTStructure, compile_jt_plan, compile_ve_plan, evidence_to_states
 
-from helpers import (SIX_NODE_ANSWERS, SNOW_ANSWERS, bp_reference_tolerance, golden_models, hostsim_run, load_golden,
+from helpers import (SIX_NODE_ANSWERS, SNOW_ANSWERS, bp_reference_tolerance, golden_models, hostsim_micro_run, hostsim_run, load_golden,
                      rel_err, six_node_net, snow_net)
 
 ALL_MODELS = ["asia", "cancer", "sachs", "child", "alarm", "hepar2", "win95pts", "pathfinder", "munin", "diabetes"]
@@ -77,7 +77,7 @@ def test_ve_plans_match_reference_golden(name):
 
 
 @pytest.mark.parametrize("name", [n for n in golden_models() if n not in ("sachs", "munin", "diabetes")])
-@pytest.mark.parametrize("distribute", ["auto", "ss", "divide"])
+@pytest.mark.parametrize("distribute", ["auto", "ss", "belief", "divide"])
 def test_jt_plans_match_reference_golden(name, distribute):
     g = load_golden(name)
     m = px.get_example_model(name)
@@ -180,3 +180,20 @@ def test_evidence_sampler_is_deterministic_and_possible():
     plan = compile_jt_plan(JTStructure.from_model(m), ev1)
     out = run_plan(plan.pool, plan.const_blob, s1)
     assert np.isfinite(out).all()  # forward-sampled evidence always has P(e) > 0
+
+
+@pytest.mark.parametrize("name", ["asia", "alarm", "hepar2", "win95pts", "pathfinder"])
+def test_microprogram_tables_match_plan_interpreter(name):
+    """Offset tables / level partition / column map built by pgx_fused.cuh::build_micro, walked on the CPU."""
+    m = px.get_example_model(name)
+    jt = JTStructure.from_model(m)
+    ev_vars, states = sample_evidence(m, 9 if name != "pathfinder" else 2, 2 if name == "asia" else 5, seed=6)
+    for distribute in ("ss", "auto", "divide"):
+        plan = compile_jt_plan(jt, ev_vars, distribute=distribute)
+        got, n_levels = hostsim_micro_run(plan, states)
+        assert n_levels == max(st.level for st in plan.steps) + 1
+        assert rel_err(got, run_plan(plan.pool, plan.const_blob, states)) <= 1e-13
+    free = [v for v in sorted(m.nodes()) if v not in ev_vars]
+    plan = compile_ve_plan(m, free[:3], ev_vars, joint=False)
+    got, _ = hostsim_micro_run(plan, states)
+    assert rel_err(got, run_plan(plan.pool, plan.const_blob, states)) <= 1e-13
