@@ -45,22 +45,32 @@ using namespace pgx;
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
+// K2. Thread = (run of `opt` consecutive output entries, evidence set); lanes of a warp = 32 consecutive evidence
+// sets at the same entries, so every access is a 256-byte (fp64) row segment whatever the strides are.
 template <typename T, int MAXK>
 __global__ void __launch_bounds__(256) k_contract_step(const int32_t* __restrict__ pool, int rec_off, int rec_len,
                                                        int ev_card_off, const T* __restrict__ cst, T* __restrict__ ws,
                                                        const int32_t* __restrict__ ev, int n_ev, int64_t B, int64_t ldb,
-                                                       int bt_log2) {
+                                                       int bt_log2, int opt) {
     extern __shared__ int32_t s_rec[];
     for (int i = threadIdx.x; i < rec_len; i += blockDim.x) s_rec[i] = pool[rec_off + i];
     __syncthreads();
     const uint32_t bt_mask = (1u << bt_log2) - 1u;
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t b = (int64_t)blockIdx.y * (bt_mask + 1u) + (t & bt_mask);
-    const uint64_t o = t >> bt_log2;
+    const uint64_t o0 = (t >> bt_log2) * (uint64_t)opt;
     const uint64_t out_size = (uint64_t)ld_i64(s_rec + 4);
-    if (b >= B || o >= out_size) return;
-    const T v = contract_elem<T, MAXK>(s_rec, cst, ws, ev + b * n_ev, pool + ev_card_off, ldb, b, (uint32_t)o);
-    ws[(ld_i64(s_rec + 8) + (int64_t)o) * ldb + b] = v;
+    if (b >= B || o0 >= out_size) return;
+    const uint64_t o1 = o0 + opt < out_size ? o0 + opt : out_size;
+    T* out = ws + ld_i64(s_rec + 8) * ldb + b;
+    if (MAXK <= 8) {
+        contract_run<T, (MAXK <= 8 ? MAXK : 8)>(s_rec, cst, ws, ev + b * n_ev, pool + ev_card_off, ldb, b, (uint32_t)o0,
+                                                (uint32_t)o1, out);
+    } else {
+        for (uint64_t o = o0; o < o1; ++o)
+            out[(int64_t)o * ldb] =
+                contract_elem<T, MAXK>(s_rec, cst, ws, ev + b * n_ev, pool + ev_card_off, ldb, b, (uint32_t)o);
+    }
 }
 
 template <typename T>
@@ -474,11 +484,15 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
         if (b_tiles > 65535) return fail(PGX_ERR_UNSUPPORTED, "batch too large for one stepwise launch (max 2,097,120)");
         const int per_block = 256 >> bt_log2;
         for (const StepInfo& s : pl->steps) {
-            dim3 grid((unsigned)((s.out_size + per_block - 1) / per_block), (unsigned)b_tiles);
+            // consecutive entries per thread: as many as leave >= ~4 waves of CTAs on 148 SMs
+            int64_t opt = (s.out_size * b_tiles) / (per_block * 148LL * 8 * 4);
+            opt = opt < 1 ? 1 : (opt > 16 ? 16 : opt);
+            const int64_t runs = (s.out_size + opt - 1) / opt;
+            dim3 grid((unsigned)((runs + per_block - 1) / per_block), (unsigned)b_tiles);
             const size_t smem = (size_t)s.rec_len * sizeof(int32_t);
 #define PGX_LAUNCH_STEP(MK)                                                                                      \
     k_contract_step<T, MK><<<grid, 256, smem, st>>>(pl->d_pool, s.rec_off, s.rec_len, pl->ev_card_off, cst, ws, ev, \
-                                                    pl->n_ev, B, ldb, bt_log2)
+                                                    pl->n_ev, B, ldb, bt_log2, (int)opt)
             if (s.n_ops <= 2)
                 PGX_LAUNCH_STEP(2);
             else if (s.n_ops <= 4)

@@ -197,6 +197,19 @@ class PlanBuilder:
         return t
 
     # ---- steps -----------------------------------------------------------------------------
+    # cost-model knobs of contract()
+    SPLIT_MIN_JOINT = 1 << 17  # steps smaller than this are never split
+    SPLIT_MIN_OUT = 2048       # ... and a step should expose at least this many output entries to the grid
+
+    def _free(self, t: Table) -> List[Hashable]:
+        return [v for v in t.vars if v not in self.ev_slot]
+
+    def _prod(self, vars_) -> int:
+        s = 1
+        for v in vars_:
+            s *= self.card[v]
+        return s
+
     def contract(
         self,
         operands: Sequence[Table],
@@ -204,39 +217,89 @@ class PlanBuilder:
         divisors: Sequence[Table] = (),
         reduce_max: bool = False,
         level: int = 0,
+        optimize: bool = True,
     ) -> Table:
-        """out[out_vars] = reduce over every other non-evidence variable of prod(operands) / prod(divisors)."""
+        """out[out_vars] = reduce over every other non-evidence variable of prod(operands) / prod(divisors).
+
+        With optimize=True the product is first re-associated greedily (like the pairwise path the reference
+        gets from opt_einsum's "greedy", pgmpy/inference/ExactInference.py:404): two operands are multiplied in
+        a cheap step of their own (summing variables nobody else needs) whenever that is cheaper than dragging
+        one more operand through the final pass; and a final pass with few output entries but a huge summed
+        range is cut in two (partial sums over an enlarged output, then a small reduce) so the grid has work."""
         out_vars = tuple(out_vars)
         ops = list(operands)
-        # split wide products so that no step exceeds MAX_OPS operands (divisors count)
+        needed_later = set(out_vars)
+        for d in divisors:
+            needed_later |= set(self._free(d))
+
+        def union_scope(tables):
+            sc: List[Hashable] = []
+            for t in tables:
+                for v in self._free(t):
+                    if v not in sc:
+                        sc.append(v)
+            return sc
+
+        if optimize and len(ops) > 2:
+            while len(ops) > 2:
+                final_joint = self._prod(union_scope(ops))
+                count: Dict[Hashable, int] = {}
+                for t in ops:
+                    for v in self._free(t):
+                        count[v] = count.get(v, 0) + 1
+                best = None
+                for i in range(len(ops)):
+                    fi = self._free(ops[i])
+                    si = set(fi)
+                    for j in range(i + 1, len(ops)):
+                        fj = self._free(ops[j])
+                        u = fi + [v for v in fj if v not in si]
+                        cost = self._prod(u)
+                        if 2 * cost >= final_joint:
+                            continue
+                        keep = [v for v in u if v in needed_later or count[v] > (1 if v in si else 0) + (1 if v in fj else 0)]
+                        key = (self._prod(keep), cost)
+                        if best is None or key < best[0]:
+                            best = (key, i, j, keep)
+                if best is None:
+                    break
+                _, i, j, keep = best
+                merged = self.contract([ops[i], ops[j]], keep, reduce_max=reduce_max, level=level, optimize=False)
+                ops = [t for k, t in enumerate(ops) if k not in (i, j)] + [merged]
+        # hard limit of the kernels: no step exceeds MAX_OPS operands (divisors count)
         while len(ops) + len(divisors) > MAX_OPS:
-            take = MAX_OPS
             ops.sort(key=lambda t: t.size)
-            group, ops = ops[:take], ops[take:]
-            scope = []
-            for t in group:
-                for v in t.vars:
-                    if v not in self.ev_slot and v not in scope:
-                        scope.append(v)
-            # variables that appear nowhere else may be reduced right here
-            later = set(out_vars)
-            for t in list(ops) + list(divisors):
+            group, ops = ops[:MAX_OPS], ops[MAX_OPS:]
+            later = set(needed_later)
+            for t in ops:
                 later |= set(t.vars)
-            keep = [v for v in scope if v in later]
-            ops.append(self.contract(group, keep, reduce_max=reduce_max, level=level))
-        scope = []
-        for t in ops:
-            for v in t.vars:
-                if v not in self.ev_slot and v not in scope:
-                    scope.append(v)
+            keep = [v for v in union_scope(group) if v in later]
+            ops.append(self.contract(group, keep, reduce_max=reduce_max, level=level, optimize=False))
+        scope = union_scope(ops)
         for v in out_vars:
             if v not in scope:
                 raise ValueError(f"output variable {v} is not in any operand")
         for d in divisors:
-            for v in d.vars:
-                if v not in self.ev_slot and v not in out_vars:
+            for v in self._free(d):
+                if v not in out_vars:
                     raise ValueError("divisor scope must be within the output scope")
         sum_vars = tuple(v for v in scope if v not in out_vars)
+        if optimize and sum_vars:
+            out_size = self._prod(out_vars)
+            joint = out_size * self._prod(sum_vars)
+            if joint >= self.SPLIT_MIN_JOINT and out_size < self.SPLIT_MIN_OUT:
+                # keep some summed variables as extra output axes of a partial step
+                keep: List[Hashable] = []
+                size = out_size
+                for v in sorted(sum_vars, key=lambda v: -self.card[v]):
+                    if size >= self.SPLIT_MIN_OUT:
+                        break
+                    keep.append(v)
+                    size *= self.card[v]
+                if keep and len(keep) < len(sum_vars):
+                    partial = self.contract(ops, out_vars + tuple(keep), reduce_max=reduce_max, level=level, optimize=False)
+                    return self.contract([partial], out_vars, divisors=divisors, reduce_max=reduce_max, level=level,
+                                         optimize=False)
         out = self.new_work(out_vars)
         idx = len(self.steps)
         self.steps.append(

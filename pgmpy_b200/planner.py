@@ -446,6 +446,9 @@ def compile_jt_plan(
     for i, c in enumerate(free):
         for v in c:
             holders.setdefault(v, []).append(i)
+    HIER_MIN = 4096  # tables at least this large hand out their single-variable marginals by recursive halving
+    result: Dict[Hashable, Table] = {}
+    from_clique: Dict[int, List[Hashable]] = {}
     for v in variables:
         if v in evset:
             raise ValueError(f"{v} is observed")
@@ -464,12 +467,40 @@ def compile_jt_plan(
                     best = cand
         _, kind, i = best
         if kind == 1:
-            t = b.contract([up[i], down[i]], [v], level=final_level)
+            result[v] = b.contract([up[i], down[i]], [v], level=final_level)
+        elif fsize(free[i]) >= HIER_MIN:
+            from_clique.setdefault(i, []).append(v)
         elif i in belief:
-            t = b.contract([belief[i]], [v], level=final_level)
+            result[v] = b.contract([belief[i]], [v], level=final_level)
         else:
-            t = b.contract([psi[i]] + incoming(i), [v], level=final_level)
-        b.emit(t, normalize, [v])
+            result[v] = b.contract([psi[i]] + incoming(i), [v], level=final_level)
+
+    def halve(table: Table, scope: List[Hashable], needed: List[Hashable]):
+        """All single-variable marginals of `needed` out of one big table in ~2 passes over it (each half of the
+        scope is summed out once, recursively) instead of one full pass per variable."""
+        if not needed:
+            return
+        if len(needed) == 1 or fsize(scope) < HIER_MIN or len(scope) < 2:
+            for v in needed:
+                result[v] = b.contract([table], [v], level=final_level)
+            return
+        total = float(np.sum([np.log(card[v]) for v in scope]))
+        acc, cut = 0.0, 1
+        for idx, v in enumerate(scope[:-1]):
+            acc += float(np.log(card[v]))
+            cut = idx + 1
+            if acc >= total / 2:
+                break
+        for part in (scope[:cut], scope[cut:]):
+            sub_needed = [v for v in needed if v in part]
+            if sub_needed:
+                halve(b.contract([table], part, level=final_level), list(part), sub_needed)
+
+    for i, vs in from_clique.items():
+        src = belief[i] if i in belief else b.contract([psi[i]] + incoming(i), free[i], level=final_level)
+        halve(src, list(free[i]), vs)
+    for v in variables:
+        b.emit(result[v], normalize, [v])
     return b.finalize(
         {"mode": "jt", "evidence_vars": tuple(ev), "variables": tuple(variables), "root": jt.root, "n_cliques": n,
          "distribute": distribute}

@@ -97,7 +97,7 @@ def rel_err(got, want):
 _hostsim = None
 
 
-def hostsim_run(plan, ev, dtype=np.float64):
+def hostsim_run(plan, ev, dtype=np.float64, use_run=True):
     """Runs the device element function (pgx_step.cuh) compiled for the host over a packed plan."""
     global _hostsim
     if _hostsim is None:
@@ -111,7 +111,7 @@ def hostsim_run(plan, ev, dtype=np.float64):
     out = np.zeros((B, plan.out_elems), dtype=dtype)
     fn = _hostsim.hostsim_run_f64 if dtype == np.float64 else _hostsim.hostsim_run_f32
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    fn(p(pool), p(cst), p(ev), p(ws), p(out), C.c_int64(B), C.c_int64(ldb))
+    fn(p(pool), p(cst), p(ev), p(ws), p(out), C.c_int64(B), C.c_int64(ldb), C.c_int(1 if use_run else 0))
     return out
 
 

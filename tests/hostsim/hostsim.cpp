@@ -9,7 +9,7 @@
 using namespace pgx;
 
 template <typename T>
-static void run(const int32_t* pool, const T* cst, const int32_t* ev, T* ws, T* out, int64_t B, int64_t ldb) {
+static void run(const int32_t* pool, const T* cst, const int32_t* ev, T* ws, T* out, int64_t B, int64_t ldb, bool use_run) {
     const int n_ev = pool[2], n_steps = pool[3], n_segs = pool[4];
     const int64_t out_elems = pool[5];
     const int32_t* index = pool + pool[10];
@@ -18,9 +18,17 @@ static void run(const int32_t* pool, const T* cst, const int32_t* ev, T* ws, T* 
         const int32_t* rec = pool + index[s];
         const uint32_t out_size = (uint32_t)rec[4];
         const int64_t out_off = ld_i64(rec + 8);
-        for (uint32_t o = 0; o < out_size; ++o)
+        if (use_run && rec[2] <= 8) {
+            // the stepwise kernel's path: runs of consecutive entries with incremental offsets (run length 5)
             for (int64_t b = 0; b < B; ++b)
-                ws[(out_off + o) * ldb + b] = contract_elem_upto<T, MAX_OPS>(rec, cst, ws, ev + b * n_ev, ev_card, ldb, b, o);
+                for (uint32_t o0 = 0; o0 < out_size; o0 += 5)
+                    contract_run<T, 8>(rec, cst, ws, ev + b * n_ev, ev_card, ldb, b, o0, o0 + 5 < out_size ? o0 + 5 : out_size,
+                                       ws + out_off * ldb + b);
+        } else {
+            for (uint32_t o = 0; o < out_size; ++o)
+                for (int64_t b = 0; b < B; ++b)
+                    ws[(out_off + o) * ldb + b] = contract_elem_upto<T, MAX_OPS>(rec, cst, ws, ev + b * n_ev, ev_card, ldb, b, o);
+        }
     }
     const int32_t* segs = pool + pool[11];
     for (int g = 0; g < n_segs; ++g) {
@@ -38,12 +46,12 @@ static void run(const int32_t* pool, const T* cst, const int32_t* ev, T* ws, T* 
 }
 
 extern "C" void hostsim_run_f64(const int32_t* pool, const double* cst, const int32_t* ev, double* ws, double* out,
-                                int64_t B, int64_t ldb) {
-    run<double>(pool, cst, ev, ws, out, B, ldb);
+                                int64_t B, int64_t ldb, int use_run) {
+    run<double>(pool, cst, ev, ws, out, B, ldb, use_run != 0);
 }
 extern "C" void hostsim_run_f32(const int32_t* pool, const float* cst, const int32_t* ev, float* ws, float* out, int64_t B,
-                                int64_t ldb) {
-    run<float>(pool, cst, ev, ws, out, B, ldb);
+                                int64_t ldb, int use_run) {
+    run<float>(pool, cst, ev, ws, out, B, ldb, use_run != 0);
 }
 
 // ---- microprogram (pgx_fused.cuh::build_micro) walked on the CPU: checks the offset tables, the level

@@ -349,3 +349,22 @@ def test_discrete_factor_algebra_vectors(torch_cuda):
     mx = DiscreteFactor(["x1", "x2", "x3"], [3, 2, 2], [0.25, 0.35, 0.08, 0.16, 0.05, 0.07, 0.00, 0.00, 0.15, 0.21, 0.08, 0.18])
     np.testing.assert_array_equal(mx.maximize(["x2"], inplace=False).values, [[0.25, 0.35], [0.05, 0.07], [0.15, 0.21]])
     assert a == DiscreteFactor(["x2", "x1"], [2, 2], a.values.T)
+
+
+def test_run_pinned_pipeline_matches_device_run(torch_cuda):
+    """End-to-end path (pinned host buffers, chunked over a stream ring) == device-resident path, bit for bit."""
+    torch = torch_cuda
+    from pgmpy_b200.inference import BeliefPropagation
+
+    m = px.get_example_model("alarm")
+    bp = BeliefPropagation(m)
+    B = 40000  # not a multiple of the chunk size
+    ev_vars, states = sample_evidence(m, B, 5, seed=11)
+    cp = bp.marginals_plan(ev_vars)
+    want = cp.run(torch.from_numpy(states).cuda()).cpu()
+    ev_pin = torch.from_numpy(states).pin_memory()
+    out_pin = torch.empty((B, cp.out_elems), dtype=torch.float64).pin_memory()
+    for chunks in (0, 1, 3, 7):
+        out_pin.zero_()
+        cp.run_pinned(ev_pin, out_pin, chunks)
+        assert torch.equal(out_pin, want)

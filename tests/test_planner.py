@@ -123,8 +123,9 @@ def test_hostsim_element_function_matches_plan_interpreter(name):
     for distribute in ("auto", "divide"):
         plan = compile_jt_plan(jt, ev_vars, distribute=distribute)
         want = run_plan(plan.pool, plan.const_blob, states)
-        got = hostsim_run(plan, states)
-        assert rel_err(got, want) <= 1e-13
+        for use_run in (True, False):  # contract_run (stepwise kernel) and contract_elem (generic fused kernel)
+            got = hostsim_run(plan, states, use_run=use_run)
+            assert rel_err(got, want) <= 1e-13
     free = [v for v in sorted(m.nodes()) if v not in ev_vars]
     plan = compile_ve_plan(m, free[:2], ev_vars, joint=True)
     assert rel_err(hostsim_run(plan, states), run_plan(plan.pool, plan.const_blob, states)) <= 1e-13
@@ -188,7 +189,7 @@ def test_microprogram_tables_match_plan_interpreter(name):
     m = px.get_example_model(name)
     jt = JTStructure.from_model(m)
     ev_vars, states = sample_evidence(m, 9 if name != "pathfinder" else 2, 2 if name == "asia" else 5, seed=6)
-    for distribute in ("ss", "auto", "divide"):
+    for distribute in (("ss", "auto", "divide") if name != "pathfinder" else ("belief",)):
         plan = compile_jt_plan(jt, ev_vars, distribute=distribute)
         got, n_levels = hostsim_micro_run(plan, states)
         assert n_levels == max(st.level for st in plan.steps) + 1
