@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--mode", default="auto", choices=["auto", "fused", "stepwise"])
     ap.add_argument("--fused-warps", type=int, default=0)
     ap.add_argument("--fused-kernel", default="auto", choices=["auto", "generic", "tables-smem", "tables-global"])
+    ap.add_argument("--step-kernel", default="auto", choices=["auto", "generic"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -270,7 +271,7 @@ def run_b200(args):
     # same evidence-variable set on every rank; each rank draws its own shard of evidence sets
     ev_vars, _ = sample_evidence(model, 1, k, seed=1)
     cp = bp.marginals_plan(ev_vars)
-    cp.set_mode(args.mode, args.fused_warps, args.fused_kernel)
+    cp.set_mode(args.mode, args.fused_warps, args.fused_kernel, args.step_kernel)
     n_batches = 2
     shards = []
     for j in range(n_batches):

@@ -62,6 +62,8 @@ extern "C" {
 #define PGX_OPT_FUSED_KERNEL 4 /* 0 auto | 1 generic addressing | 2 offset tables + shared-memory work tables |
                                   3 offset tables + global work tables */
 
+#define PGX_OPT_STEP_KERNEL 5  /* stepwise mode: 0 auto (tile-cooperative kernel where its tables fit) | 1 generic only */
+
 #define PGX_INFO_N_STEPS 1
 #define PGX_INFO_OUT_ELEMS 2
 #define PGX_INFO_WS_ENTRIES 3
@@ -69,6 +71,7 @@ extern "C" {
 #define PGX_INFO_LAST_MODE 5
 #define PGX_INFO_N_EV 6
 #define PGX_INFO_LAST_VARIANT 7 /* which fused kernel ran (PGX_OPT_FUSED_KERNEL numbering), 0 if stepwise */
+#define PGX_INFO_LAST_GRAPH 9    /* 1 if the most recent stepwise run was a CUDA-graph replay */
 #define PGX_INFO_N_LEVELS 8     /* dependency levels of the plan (0 when no offset tables were built) */
 
 typedef struct pgx_plan pgx_plan; /* opaque */

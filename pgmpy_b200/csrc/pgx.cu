@@ -73,6 +73,156 @@ __global__ void __launch_bounds__(256) k_contract_step(const int32_t* __restrict
     }
 }
 
+// K2, tile-cooperative form (the default for steps whose summed range fits the shared offset table).
+// ncu on munin showed the per-thread mixed-radix decomposition costs ~150 issue slots per (entry, warp): SIMT lanes
+// of a warp all decode the SAME entry. Here a CTA owns a tile of `TO` consecutive output entries and up to `btb`
+// tiles of 32 evidence sets:
+//   phase 1  thread t decodes entry tile0 + t ONCE for the whole CTA -> s_otab[t][k]; the summed range is decoded the
+//            same way into s_stab[q][k]  (lanes work on different entries: no redundant index arithmetic);
+//   phase 2  lanes = evidence sets again; a warp streams rows  sum_q prod_k operand_k[(otab + stab) * unit]  with
+//            nothing but shared-memory offset reads, one IMAD.WIDE, the load and the multiply per operand.
+template <typename T, int MAXK>
+__global__ void __launch_bounds__(256) k_contract_tile(const int32_t* __restrict__ pool, int rec_off, int rec_len,
+                                                       int ev_card_off, const T* __restrict__ cst, T* __restrict__ ws,
+                                                       const int32_t* __restrict__ ev, int n_ev, int64_t B, int64_t ldb,
+                                                       int bt_log2, int TO, int btb) {
+    extern __shared__ int32_t s_mem[];
+    int32_t* s_rec = s_mem;
+    for (int i = threadIdx.x; i < rec_len; i += blockDim.x) s_rec[i] = pool[rec_off + i];
+    __syncthreads();
+    const int A = s_rec[0], S = s_rec[1], K = s_rec[2], flags = s_rec[3];
+    const int opw = OP_FIXED + A + S;
+    const int32_t* odims = s_rec + STEP_FIXED;
+    const int32_t* sdims = odims + A;
+    const int32_t* ops = sdims + S;
+    const uint32_t out_size = (uint32_t)s_rec[4];
+    const int sum_size = s_rec[6];
+    int32_t* s_otab = s_mem + ((rec_len + 3) & ~3);
+    int32_t* s_stab = s_otab + TO * K;
+    const uint32_t tile0 = blockIdx.x * (uint32_t)TO;
+    for (int t = threadIdx.x; t < TO; t += blockDim.x) {
+        uint32_t rem = tile0 + t;
+        int32_t off[MAXK];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) off[k] = 0;
+        if (rem < out_size) {
+            for (int a = A - 1; a >= 0; --a) {
+                const uint32_t d = (uint32_t)odims[a];
+                const uint32_t q = rem / d;
+                const int32_t digit = (int32_t)(rem - q * d);
+                rem = q;
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k)
+                    if (k < K) off[k] += digit * ops[k * opw + OP_FIXED + a];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+            if (k < K) s_otab[t * K + k] = off[k];
+    }
+    for (int qi = threadIdx.x; qi < sum_size; qi += blockDim.x) {
+        uint32_t rem = (uint32_t)qi;
+        int32_t off[MAXK];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) off[k] = 0;
+        for (int a = S - 1; a >= 0; --a) {
+            const uint32_t d = (uint32_t)sdims[a];
+            const uint32_t q = rem / d;
+            const int32_t digit = (int32_t)(rem - q * d);
+            rem = q;
+#pragma unroll
+            for (int k = 0; k < MAXK; ++k)
+                if (k < K) off[k] += digit * ops[k * opw + OP_FIXED + A + a];
+        }
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+            if (k < K) s_stab[qi * K + k] = off[k];
+    }
+    __syncthreads();
+
+    int n_mul = K;
+    if (flags & FLAG_DIV)
+        while (n_mul > 0 && (ops[(n_mul - 1) * opw] & 0x100)) --n_mul;
+    const bool use_max = (flags & FLAG_MAX) != 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int bt = 1 << bt_log2;
+    const int o_per_warp = 32 >> bt_log2;         // entries a warp covers at once when the batch is narrower than 32
+    const int o_sub = lane >> bt_log2;
+    const int64_t out_off = ld_i64(s_rec + 8);
+    const int32_t* ev_card = pool + ev_card_off;
+    for (int tb = 0; tb < btb; ++tb) {
+        const int64_t b = ((int64_t)blockIdx.y * btb + tb) * bt + (lane & (bt - 1));
+        if (b >= B) continue;  // whole (sub-)warp shares b-validity only per lane group; no barriers below
+        const T* base[MAXK];
+        int64_t unit[MAXK];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) {
+            base[k] = cst;
+            unit[k] = 1;
+            if (k < K) {
+                const int32_t* op = ops + k * opw;
+                int64_t e = ld_i64(op + 1);
+                const int ne = op[3];
+                if (ne > 0) {
+                    const int32_t* pairs = s_rec + op[4];
+                    for (int j = 0; j < ne; ++j) {
+                        const int slot = pairs[2 * j];
+                        int32_t st = ev[b * n_ev + slot];
+                        const int32_t card = ev_card[slot];
+                        st = st < 0 ? 0 : (st >= card ? card - 1 : st);
+                        e += st * pairs[2 * j + 1];
+                    }
+                }
+                if ((op[0] & 0xFF) == 1) {
+                    unit[k] = ldb;
+                    base[k] = ws + e * ldb + b;
+                } else {
+                    base[k] = cst + e;
+                }
+            }
+        }
+        T* out = ws + out_off * ldb + b;
+        for (int og = warp * o_per_warp + o_sub; og < TO; og += n_warps * o_per_warp) {
+            const uint32_t o = tile0 + og;
+            if (o >= out_size) break;
+            const int32_t* ot = s_otab + og * K;
+            const T* ptr[MAXK];
+#pragma unroll
+            for (int k = 0; k < MAXK; ++k) ptr[k] = (k < K) ? base[k] + (int64_t)ot[k] * unit[k] : base[k];
+            T acc;
+            if (S == 0) {
+                T prod = (T)1;
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k)
+                    if (k < n_mul) prod *= *ptr[k];
+                acc = prod;
+            } else {
+                acc = use_max ? neg_inf<T>() : (T)0;
+                const int32_t* st = s_stab;
+                for (int q = 0; q < sum_size; ++q, st += K) {
+                    T prod = (T)1;
+#pragma unroll
+                    for (int k = 0; k < MAXK; ++k)
+                        if (k < n_mul) prod *= ptr[k][(int64_t)st[k] * unit[k]];
+                    if (use_max)
+                        acc = prod > acc ? prod : acc;
+                    else
+                        acc += prod;
+                }
+            }
+            if (flags & FLAG_DIV) {
+                T den = (T)1;
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k)
+                    if (k >= n_mul && k < K) den *= *ptr[k];
+                const T r = acc / den;
+                acc = (r != r) ? (T)0 : r;
+            }
+            out[(int64_t)o * ldb] = acc;
+        }
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ void emit_segment(const int32_t* __restrict__ seg, const T* __restrict__ ws,
                                              T* __restrict__ out, int64_t out_elems, int64_t ldb, int64_t b) {
@@ -186,6 +336,17 @@ int ilog2_floor(int64_t x) {
 
 }  // namespace
 
+struct GraphEntry {
+    int64_t B;
+    const void* ev;
+    void* out;
+    void* ws;
+    int step_kernel;
+    int dtype_size;
+    int n_launches;
+    cudaGraphExec_t exec;
+};
+
 struct pgx_plan {
     int dtype = PGX_F64;
     int device = 0;
@@ -203,6 +364,11 @@ struct pgx_plan {
     // options
     int mode = PGX_MODE_AUTO;
     int fused_warps = 0;  // 0 = auto
+    int use_graph = 1;    // stepwise: replay the step sequence as a CUDA graph
+    std::vector<GraphEntry> graphs;
+    cudaStream_t cap_stream = nullptr;
+    int last_graph = 0;
+    int step_kernel = 0;  // 0 = auto (tile-cooperative where possible), 1 = generic per-thread kernel only
     int fused_kernel = 0; // 0 = auto, 1 = generic (v1), 2 = table-driven/shared workspace, 3 = table-driven/global workspace
     int last_variant = 0;
     // info
@@ -367,6 +533,8 @@ void pgx_plan_destroy(pgx_plan* plan) {
     if (!plan) return;
     if (plan->d_pool) cudaFree(plan->d_pool);
     if (plan->d_micro) cudaFree(plan->d_micro);
+    for (GraphEntry& g : plan->graphs) cudaGraphExecDestroy(g.exec);
+    if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
     delete plan;
 }
 
@@ -387,6 +555,13 @@ int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
             if (value < 0 || value > 16) return fail(PGX_ERR_INVALID, "fused warps must be 0..16");
             plan->fused_warps = (int)value;
             return PGX_OK;
+        case PGX_OPT_USE_GRAPH:
+            plan->use_graph = value ? 1 : 0;
+            return PGX_OK;
+        case PGX_OPT_STEP_KERNEL:
+            if (value < 0 || value > 1) return fail(PGX_ERR_INVALID, "step kernel must be 0 or 1");
+            plan->step_kernel = (int)value;
+            return PGX_OK;
         case PGX_OPT_FUSED_KERNEL:
             if (value < 0 || value > 3) return fail(PGX_ERR_INVALID, "fused kernel must be 0..3");
             plan->fused_kernel = (int)value;
@@ -406,6 +581,7 @@ int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value) {
         case PGX_INFO_LAST_MODE: *value = plan->last_mode; break;
         case PGX_INFO_N_EV: *value = plan->n_ev; break;
         case PGX_INFO_LAST_VARIANT: *value = plan->last_variant; break;
+        case PGX_INFO_LAST_GRAPH: *value = plan->last_graph; break;
         case PGX_INFO_N_LEVELS: *value = plan->micro.ok ? plan->micro.n_levels : 0; break;
         default: return fail(PGX_ERR_UNSUPPORTED, "unknown info key");
     }
@@ -483,35 +659,105 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
         const int64_t b_tiles = (B + bt - 1) / bt;
         if (b_tiles > 65535) return fail(PGX_ERR_UNSUPPORTED, "batch too large for one stepwise launch (max 2,097,120)");
         const int per_block = 256 >> bt_log2;
+        auto enqueue = [&](cudaStream_t qs) -> int {
+            int64_t n = 0;
+            int64_t& launches = n;
         for (const StepInfo& s : pl->steps) {
-            // consecutive entries per thread: as many as leave >= ~4 waves of CTAs on 148 SMs
-            int64_t opt = (s.out_size * b_tiles) / (per_block * 148LL * 8 * 4);
-            opt = opt < 1 ? 1 : (opt > 16 ? 16 : opt);
-            const int64_t runs = (s.out_size + opt - 1) / opt;
-            dim3 grid((unsigned)((runs + per_block - 1) / per_block), (unsigned)b_tiles);
-            const size_t smem = (size_t)s.rec_len * sizeof(int32_t);
+                // tile-cooperative kernel when the summed range's offset table fits shared memory
+                const int64_t stab_words = s.sum_size * s.n_ops;
+                if (s.n_ops <= 8 && stab_words <= 8192 && pl->step_kernel != 1) {
+                    const int o_per_warp = 32 >> bt_log2;
+                    int btb = (int)(b_tiles < 4 ? b_tiles : 4);
+                    const int64_t b_blocks = (b_tiles + btb - 1) / btb;
+                    int64_t TO = (s.out_size * b_blocks) / (148 * 4);  // aim at >= 4 CTAs per SM when there is work
+                    TO = TO < 8 * o_per_warp ? 8 * o_per_warp : (TO > 512 ? 512 : TO);
+                    if (TO * s.n_ops > 2048) TO = 2048 / s.n_ops;
+                    TO = (TO + o_per_warp - 1) / o_per_warp * o_per_warp;
+                    if (TO > s.out_size) TO = (s.out_size + o_per_warp - 1) / o_per_warp * o_per_warp;
+                    dim3 grid((unsigned)((s.out_size + TO - 1) / TO), (unsigned)b_blocks);
+                    const size_t smem = (size_t)(((s.rec_len + 3) & ~3) + TO * s.n_ops + stab_words) * sizeof(int32_t);
+#define PGX_LAUNCH_TILE(MK)                                                                                          \
+    k_contract_tile<T, MK><<<grid, 256, smem, qs>>>(pl->d_pool, s.rec_off, s.rec_len, pl->ev_card_off, cst, ws, ev, \
+                                                        pl->n_ev, B, ldb, bt_log2, (int)TO, btb)
+                    if (s.n_ops <= 2)
+                        PGX_LAUNCH_TILE(2);
+                    else if (s.n_ops <= 4)
+                        PGX_LAUNCH_TILE(4);
+                    else
+                        PGX_LAUNCH_TILE(8);
+#undef PGX_LAUNCH_TILE
+                    ++launches;
+                    continue;
+                }
+                // generic kernel: consecutive entries per thread, as many as leave >= ~4 waves of CTAs on 148 SMs
+                int64_t opt = (s.out_size * b_tiles) / (per_block * 148LL * 8 * 4);
+                opt = opt < 1 ? 1 : (opt > 16 ? 16 : opt);
+                const int64_t runs = (s.out_size + opt - 1) / opt;
+                dim3 grid((unsigned)((runs + per_block - 1) / per_block), (unsigned)b_tiles);
+                const size_t smem = (size_t)s.rec_len * sizeof(int32_t);
 #define PGX_LAUNCH_STEP(MK)                                                                                      \
-    k_contract_step<T, MK><<<grid, 256, smem, st>>>(pl->d_pool, s.rec_off, s.rec_len, pl->ev_card_off, cst, ws, ev, \
-                                                    pl->n_ev, B, ldb, bt_log2, (int)opt)
-            if (s.n_ops <= 2)
-                PGX_LAUNCH_STEP(2);
-            else if (s.n_ops <= 4)
-                PGX_LAUNCH_STEP(4);
-            else if (s.n_ops <= 8)
-                PGX_LAUNCH_STEP(8);
-            else
-                PGX_LAUNCH_STEP(MAX_OPS);
+    k_contract_step<T, MK><<<grid, 256, smem, qs>>>(pl->d_pool, s.rec_off, s.rec_len, pl->ev_card_off, cst, ws, ev, \
+                                                        pl->n_ev, B, ldb, bt_log2, (int)opt)
+                if (s.n_ops <= 2)
+                    PGX_LAUNCH_STEP(2);
+                else if (s.n_ops <= 4)
+                    PGX_LAUNCH_STEP(4);
+                else if (s.n_ops <= 8)
+                    PGX_LAUNCH_STEP(8);
+                else
+                    PGX_LAUNCH_STEP(MAX_OPS);
 #undef PGX_LAUNCH_STEP
-            ++launches;
+                ++launches;
+            }
+            if (pl->n_segs > 0) {
+                dim3 grid((unsigned)((B + 127) / 128), (unsigned)pl->n_segs);
+                if (pl->n_segs > 65535) return fail(PGX_ERR_UNSUPPORTED, "too many output segments");
+                k_emit<T><<<grid, 128, 0, qs>>>(pl->d_pool, pl->segs_off, ws, out, pl->out_elems, B, ldb);
+                ++launches;
+            }
+            return (int)n;
+        };
+        if (pl->n_segs > 65535) return fail(PGX_ERR_UNSUPPORTED, "too many output segments");
+        bool replayed = false;
+        if (pl->use_graph && pl->n_steps >= 8) {
+            // replay the launch sequence as a CUDA graph (captured once per argument tuple)
+            GraphEntry* hit = nullptr;
+            for (GraphEntry& g : pl->graphs)
+                if (g.B == B && g.ev == (const void*)ev && g.out == out_v && g.ws == ws_v && g.step_kernel == pl->step_kernel &&
+                    g.dtype_size == (int)sizeof(T))
+                    hit = &g;
+            if (!hit) {
+                if (!pl->cap_stream) PGX_CUDA(cudaStreamCreateWithFlags(&pl->cap_stream, cudaStreamNonBlocking));
+                cudaGraph_t graph = nullptr;
+                PGX_CUDA(cudaStreamBeginCapture(pl->cap_stream, cudaStreamCaptureModeThreadLocal));
+                const int n = enqueue(pl->cap_stream);
+                cudaError_t ce = cudaStreamEndCapture(pl->cap_stream, &graph);
+                if (ce == cudaSuccess && graph) {
+                    cudaGraphExec_t exec = nullptr;
+                    ce = cudaGraphInstantiate(&exec, graph, 0);
+                    cudaGraphDestroy(graph);
+                    if (ce == cudaSuccess) {
+                        if (pl->graphs.size() >= 8) {
+                            cudaGraphExecDestroy(pl->graphs.front().exec);
+                            pl->graphs.erase(pl->graphs.begin());
+                        }
+                        pl->graphs.push_back(GraphEntry{B, (const void*)ev, out_v, ws_v, pl->step_kernel, (int)sizeof(T), n, exec});
+                        hit = &pl->graphs.back();
+                    }
+                }
+                if (!hit) (void)cudaGetLastError();  // capture failed: fall through to direct launches
+            }
+            if (hit) {
+                PGX_CUDA(cudaGraphLaunch(hit->exec, st));
+                launches = hit->n_launches;
+                replayed = true;
+            }
         }
-        PGX_CUDA(cudaGetLastError());
-        if (pl->n_segs > 0) {
-            dim3 grid((unsigned)((B + 127) / 128), (unsigned)pl->n_segs);
-            if (pl->n_segs > 65535) return fail(PGX_ERR_UNSUPPORTED, "too many output segments");
-            k_emit<T><<<grid, 128, 0, st>>>(pl->d_pool, pl->segs_off, ws, out, pl->out_elems, B, ldb);
+        if (!replayed) {
+            launches = enqueue(st);
             PGX_CUDA(cudaGetLastError());
-            ++launches;
         }
+        pl->last_graph = replayed ? 1 : 0;
     }
     if (mode != PGX_MODE_FUSED) pl->last_variant = 0;
     pl->last_launches = launches;

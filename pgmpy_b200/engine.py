@@ -66,8 +66,10 @@ class CompiledPlan:
             self.handle = None
 
     # ---- options / info ----------------------------------------------------------------------
-    def set_mode(self, mode: str = "auto", fused_warps: int = 0, fused_kernel: str = "auto"):
-        """mode: auto | stepwise | fused.  fused_kernel: auto | generic | tables-smem | tables-global."""
+    def set_mode(self, mode: str = "auto", fused_warps: int = 0, fused_kernel: str = "auto", step_kernel: str = "auto"):
+        """mode: auto | stepwise | fused.  fused_kernel: auto | generic | tables-smem | tables-global.
+        step_kernel: auto (tile-cooperative where possible) | generic."""
+        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_STEP_KERNEL, {"auto": 0, "generic": 1}[step_kernel]))
         m = {"auto": N.MODE_AUTO, "stepwise": N.MODE_STEPWISE, "fused": N.MODE_FUSED}[mode]
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_MODE, m))
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_FUSED_WARPS, fused_warps))
@@ -90,6 +92,13 @@ class CompiledPlan:
     def last_variant(self) -> str:
         v = self.info(N.INFO_LAST_VARIANT)
         return {0: "stepwise", 1: "generic", 2: "tables-smem", 3: "tables-global"}[v]
+
+    def set_graph(self, enabled: bool = True):
+        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_USE_GRAPH, 1 if enabled else 0))
+
+    @property
+    def last_graph(self) -> bool:
+        return bool(self.info(N.INFO_LAST_GRAPH))
 
     def workspace_bytes(self, batch: int) -> int:
         return int(self.lib.pgx_workspace_bytes(self.handle, batch))

@@ -198,8 +198,8 @@ class PlanBuilder:
 
     # ---- steps -----------------------------------------------------------------------------
     # cost-model knobs of contract()
-    SPLIT_MIN_JOINT = 1 << 17  # steps smaller than this are never split
-    SPLIT_MIN_OUT = 2048       # ... and a step should expose at least this many output entries to the grid
+    SPLIT_MIN_JOINT = 1 << 15  # steps smaller than this are never split
+    SPLIT_MIN_OUT = 1024       # ... and a step should expose at least this many output entries to the grid
 
     def _free(self, t: Table) -> List[Hashable]:
         return [v for v in t.vars if v not in self.ev_slot]
@@ -218,6 +218,7 @@ class PlanBuilder:
         reduce_max: bool = False,
         level: int = 0,
         optimize: bool = True,
+        split: bool = True,
     ) -> Table:
         """out[out_vars] = reduce over every other non-evidence variable of prod(operands) / prod(divisors).
 
@@ -284,7 +285,7 @@ class PlanBuilder:
                 if v not in out_vars:
                     raise ValueError("divisor scope must be within the output scope")
         sum_vars = tuple(v for v in scope if v not in out_vars)
-        if optimize and sum_vars:
+        if split and sum_vars:
             out_size = self._prod(out_vars)
             joint = out_size * self._prod(sum_vars)
             if joint >= self.SPLIT_MIN_JOINT and out_size < self.SPLIT_MIN_OUT:
@@ -297,9 +298,10 @@ class PlanBuilder:
                     keep.append(v)
                     size *= self.card[v]
                 if keep and len(keep) < len(sum_vars):
-                    partial = self.contract(ops, out_vars + tuple(keep), reduce_max=reduce_max, level=level, optimize=False)
+                    partial = self.contract(ops, out_vars + tuple(keep), reduce_max=reduce_max, level=level, optimize=False,
+                                            split=False)
                     return self.contract([partial], out_vars, divisors=divisors, reduce_max=reduce_max, level=level,
-                                         optimize=False)
+                                         optimize=False, split=False)
         out = self.new_work(out_vars)
         idx = len(self.steps)
         self.steps.append(

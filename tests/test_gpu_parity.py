@@ -32,12 +32,14 @@ def _engine():
     return CompiledPlan
 
 
-EXEC_VARIANTS = [("stepwise", "auto"), ("fused", "generic"), ("fused", "tables-smem"), ("fused", "tables-global")]
+# (mode, fused kernel, step kernel)
+EXEC_VARIANTS = [("stepwise", "auto", "auto"), ("stepwise", "auto", "generic"), ("fused", "generic", "auto"),
+                 ("fused", "tables-smem", "auto"), ("fused", "tables-global", "auto")]
 
 
 @pytest.mark.parametrize("name", ["asia", "alarm", "hepar2", "win95pts"])
-@pytest.mark.parametrize("mode,kernel", EXEC_VARIANTS)
-def test_jt_all_marginals_vs_oracle(torch_cuda, name, mode, kernel):
+@pytest.mark.parametrize("mode,kernel,step_kernel", EXEC_VARIANTS)
+def test_jt_all_marginals_vs_oracle(torch_cuda, name, mode, kernel, step_kernel):
     """Same seeded evidence through every CUDA execution variant and the numpy plan interpreter; fp64, 1e-12."""
     m = px.get_example_model(name)
     jt = JTStructure.from_model(m)
@@ -46,7 +48,7 @@ def test_jt_all_marginals_vs_oracle(torch_cuda, name, mode, kernel):
         for distribute in ("ss", "belief", "divide"):
             plan = compile_jt_plan(jt, ev_vars, distribute=distribute)
             cp = _engine()(plan)
-            cp.set_mode(mode, 3 if mode == "fused" else 0, kernel)
+            cp.set_mode(mode, 3 if mode == "fused" else 0, kernel, step_kernel)
             got = cp.run_host(states)
             want = run_plan(plan.pool, plan.const_blob, states)
             assert rel_err(got, want) <= 1e-12
@@ -116,12 +118,13 @@ def test_large_models_stepwise_vs_oracle(torch_cuda, name):
     jt = JTStructure.from_model(m)
     ev_vars, states = sample_evidence(m, 3, 8, seed=2)
     plan = compile_jt_plan(jt, ev_vars)
-    cp = _engine()(plan)
-    cp.set_mode("stepwise")
-    got = cp.run_host(states)
     want = run_plan(plan.pool, plan.const_blob, states)
-    assert np.isfinite(got).all()
-    assert rel_err(got, want) <= 1e-12
+    for step_kernel in ("auto", "generic"):
+        cp = _engine()(plan)
+        cp.set_mode("stepwise", 0, "auto", step_kernel)
+        got = cp.run_host(states)
+        assert np.isfinite(got).all()
+        assert rel_err(got, want) <= 1e-12
 
 
 def test_known_answers_ve_and_bp(torch_cuda):
@@ -231,9 +234,9 @@ def test_fp32_mode_within_1e5(torch_cuda):
     ev_vars, states = sample_evidence(m, 512, 5, seed=9)
     plan = compile_jt_plan(jt, ev_vars)
     want = run_plan(plan.pool, plan.const_blob, states)
-    for mode, kernel in EXEC_VARIANTS:
+    for mode, kernel, step_kernel in EXEC_VARIANTS:
         cp = _engine()(plan, dtype="float32")
-        cp.set_mode(mode, 0, kernel)
+        cp.set_mode(mode, 0, kernel, step_kernel)
         got = cp.run_host(states)
         assert got.dtype == np.float32
         assert np.max(np.abs(got - want)) <= 1e-5
@@ -368,3 +371,30 @@ def test_run_pinned_pipeline_matches_device_run(torch_cuda):
         out_pin.zero_()
         cp.run_pinned(ev_pin, out_pin, chunks)
         assert torch.equal(out_pin, want)
+
+
+def test_cuda_graph_replay_matches_direct_launches(torch_cuda):
+    """Stepwise mode replays the step sequence as a CUDA graph when the argument tuple repeats."""
+    torch = torch_cuda
+    m = px.get_example_model("hepar2")
+    jt = JTStructure.from_model(m)
+    ev_vars, states = sample_evidence(m, 300, 8, seed=21)
+    plan = compile_jt_plan(jt, ev_vars)
+    cp = _engine()(plan)
+    cp.set_mode("stepwise")
+    ev = torch.from_numpy(states).cuda()
+    out = torch.empty((300, cp.out_elems), dtype=torch.float64, device="cuda")
+    cp.set_graph(False)
+    direct = cp.run(ev, out=out).clone()
+    assert not cp.last_graph
+    cp.set_graph(True)
+    first = cp.run(ev, out=out).clone()
+    second = cp.run(ev, out=out).clone()
+    assert cp.last_graph
+    assert torch.equal(first, direct) and torch.equal(second, direct)
+    # new evidence values through the same buffers: the replayed graph must read the new data
+    _, states2 = sample_evidence(m, 300, 8, seed=22, evidence_vars=ev_vars)
+    ev.copy_(torch.from_numpy(states2))
+    third = cp.run(ev, out=out).cpu().numpy()
+    assert cp.last_graph
+    assert rel_err(third, run_plan(plan.pool, plan.const_blob, states2)) <= 1e-12
