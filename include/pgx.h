@@ -102,6 +102,11 @@ size_t pgx_workspace_bytes(const pgx_plan* plan, int64_t B);
 int pgx_run_batch(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
                   int64_t B, void* stream);
 
+/* Tracing aid: runs the plan in stepwise mode with a CUDA event after every step and returns the per-step device
+ * time in milliseconds (step_ms[n_steps], n_steps >= the plan's step count). Synchronises the stream. */
+int pgx_profile_steps(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
+                      int64_t B, void* stream, float* step_ms, int32_t n_steps);
+
 int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value);
 int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value);
 

@@ -19,6 +19,7 @@ EXPORTS = (
     "pgx_plan_destroy",
     "pgx_workspace_bytes",
     "pgx_run_batch",
+    "pgx_profile_steps",
     "pgx_plan_set_option",
     "pgx_plan_get_info",
     "pgx_evidence_reduce",
@@ -69,6 +70,10 @@ def load():
     lib.pgx_workspace_bytes.restype = C.c_size_t
     lib.pgx_run_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p]
     lib.pgx_run_batch.restype = C.c_int
+    lib.pgx_profile_steps.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p, C.POINTER(C.c_float), C.c_int32,
+    ]
+    lib.pgx_profile_steps.restype = C.c_int
     lib.pgx_plan_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
     lib.pgx_plan_set_option.restype = C.c_int
     lib.pgx_plan_get_info.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]

@@ -73,6 +73,15 @@ __global__ void __launch_bounds__(256) k_contract_step(const int32_t* __restrict
     }
 }
 
+// One (step, tile shape) entry of a level-batched launch of k_contract_tile.
+struct TileItem {
+    int32_t rec_off, rec_len;
+    int32_t TO;        // output entries per CTA tile
+    int32_t btb;       // evidence-set tiles (of 32) per CTA
+    int32_t b_blocks;  // CTAs along the batch
+    int32_t blk_begin; // first linear CTA index of this step inside the launch
+};
+
 // K2, tile-cooperative form (the default for steps whose summed range fits the shared offset table).
 // ncu on munin showed the per-thread mixed-radix decomposition costs ~150 issue slots per (entry, warp): SIMT lanes
 // of a warp all decode the SAME entry. Here a CTA owns a tile of `TO` consecutive output entries and up to `btb`
@@ -81,14 +90,30 @@ __global__ void __launch_bounds__(256) k_contract_step(const int32_t* __restrict
 //            same way into s_stab[q][k]  (lanes work on different entries: no redundant index arithmetic);
 //   phase 2  lanes = evidence sets again; a warp streams rows  sum_q prod_k operand_k[(otab + stab) * unit]  with
 //            nothing but shared-memory offset reads, one IMAD.WIDE, the load and the multiply per operand.
+// One launch covers ALL tile-eligible steps of a dependency level (they are independent): the linear CTA index is
+// mapped to its step through `items` (binary search), so the thousands of tiny steps of a large junction tree cost
+// one launch per level instead of one launch each.
 template <typename T, int MAXK>
-__global__ void __launch_bounds__(256) k_contract_tile(const int32_t* __restrict__ pool, int rec_off, int rec_len,
-                                                       int ev_card_off, const T* __restrict__ cst, T* __restrict__ ws,
-                                                       const int32_t* __restrict__ ev, int n_ev, int64_t B, int64_t ldb,
-                                                       int bt_log2, int TO, int btb) {
+__global__ void __launch_bounds__(256) k_contract_tile(const int32_t* __restrict__ pool,
+                                                       const TileItem* __restrict__ items, int n_items, int ev_card_off,
+                                                       const T* __restrict__ cst, const T* __restrict__ ws_in,
+                                                       T* __restrict__ ws_out, const int32_t* __restrict__ ev, int n_ev,
+                                                       int64_t B, int64_t ldb, int bt_log2) {
     extern __shared__ int32_t s_mem[];
+    // which step does this CTA belong to?
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (items[mid].blk_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const TileItem it = items[lo];
+    const int local = (int)blockIdx.x - it.blk_begin;
+    const int tile_x = local / it.b_blocks;
+    const int b_block = local - tile_x * it.b_blocks;
+    const int TO = it.TO, btb = it.btb, rec_len = it.rec_len;
+
     int32_t* s_rec = s_mem;
-    for (int i = threadIdx.x; i < rec_len; i += blockDim.x) s_rec[i] = pool[rec_off + i];
+    for (int i = threadIdx.x; i < rec_len; i += blockDim.x) s_rec[i] = pool[it.rec_off + i];
     __syncthreads();
     const int A = s_rec[0], S = s_rec[1], K = s_rec[2], flags = s_rec[3];
     const int opw = OP_FIXED + A + S;
@@ -99,7 +124,7 @@ __global__ void __launch_bounds__(256) k_contract_tile(const int32_t* __restrict
     const int sum_size = s_rec[6];
     int32_t* s_otab = s_mem + ((rec_len + 3) & ~3);
     int32_t* s_stab = s_otab + TO * K;
-    const uint32_t tile0 = blockIdx.x * (uint32_t)TO;
+    const uint32_t tile0 = (uint32_t)tile_x * (uint32_t)TO;
     for (int t = threadIdx.x; t < TO; t += blockDim.x) {
         uint32_t rem = tile0 + t;
         int32_t off[MAXK];
@@ -146,13 +171,14 @@ __global__ void __launch_bounds__(256) k_contract_tile(const int32_t* __restrict
     const bool use_max = (flags & FLAG_MAX) != 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const int bt = 1 << bt_log2;
-    const int o_per_warp = 32 >> bt_log2;         // entries a warp covers at once when the batch is narrower than 32
+    const int o_per_warp = 32 >> bt_log2;  // entries a warp covers at once when the batch is narrower than 32
     const int o_sub = lane >> bt_log2;
     const int64_t out_off = ld_i64(s_rec + 8);
     const int32_t* ev_card = pool + ev_card_off;
+    const int og_step = n_warps * o_per_warp;
     for (int tb = 0; tb < btb; ++tb) {
-        const int64_t b = ((int64_t)blockIdx.y * btb + tb) * bt + (lane & (bt - 1));
-        if (b >= B) continue;  // whole (sub-)warp shares b-validity only per lane group; no barriers below
+        const int64_t b = ((int64_t)b_block * btb + tb) * bt + (lane & (bt - 1));
+        if (b >= B) continue;  // no barriers below
         const T* base[MAXK];
         int64_t unit[MAXK];
 #pragma unroll
@@ -175,14 +201,44 @@ __global__ void __launch_bounds__(256) k_contract_tile(const int32_t* __restrict
                 }
                 if ((op[0] & 0xFF) == 1) {
                     unit[k] = ldb;
-                    base[k] = ws + e * ldb + b;
+                    base[k] = ws_in + e * ldb + b;
                 } else {
                     base[k] = cst + e;
                 }
             }
         }
-        T* out = ws + out_off * ldb + b;
-        for (int og = warp * o_per_warp + o_sub; og < TO; og += n_warps * o_per_warp) {
+        T* out = ws_out + out_off * ldb + b;
+        if (S == 0 && !(flags & FLAG_DIV)) {
+            // pure product: two entries in flight per thread (the step never reads what it writes, so the loads of
+            // the second entry may be issued before the store of the first)
+            for (int og = warp * o_per_warp + o_sub; og < TO; og += 2 * og_step) {
+                const uint32_t o0 = tile0 + og, o1 = o0 + og_step;
+                if (o0 >= out_size) break;
+                const bool two = (og + og_step < TO) && (o1 < out_size);
+                const int32_t* ot0 = s_otab + og * K;
+                const int32_t* ot1 = ot0 + (two ? og_step * K : 0);
+                T v0[MAXK], v1[MAXK];
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k) {
+                    if (k < K) {
+                        v0[k] = base[k][(int64_t)ot0[k] * unit[k]];
+                        v1[k] = base[k][(int64_t)ot1[k] * unit[k]];
+                    }
+                }
+                T p0 = (T)1, p1 = (T)1;
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k) {
+                    if (k < K) {
+                        p0 *= v0[k];
+                        p1 *= v1[k];
+                    }
+                }
+                out[(int64_t)o0 * ldb] = p0;
+                if (two) out[(int64_t)o1 * ldb] = p1;
+            }
+            continue;
+        }
+        for (int og = warp * o_per_warp + o_sub; og < TO; og += og_step) {
             const uint32_t o = tile0 + og;
             if (o >= out_size) break;
             const int32_t* ot = s_otab + og * K;
@@ -199,6 +255,7 @@ __global__ void __launch_bounds__(256) k_contract_tile(const int32_t* __restrict
             } else {
                 acc = use_max ? neg_inf<T>() : (T)0;
                 const int32_t* st = s_stab;
+#pragma unroll 4
                 for (int q = 0; q < sum_size; ++q, st += K) {
                     T prod = (T)1;
 #pragma unroll
@@ -326,6 +383,7 @@ struct StepInfo {
     int64_t out_size;
     int64_t sum_size;
     int n_ops;
+    int level;
 };
 
 int ilog2_floor(int64_t x) {
@@ -335,6 +393,19 @@ int ilog2_floor(int64_t x) {
 }
 
 }  // namespace
+
+struct LaunchGroup {
+    int generic_step = -1;  // >= 0: one launch of the generic kernel for this step
+    int first_item = 0, n_items = 0, n_blocks = 0, max_k = 0;
+    size_t smem = 0;
+};
+
+struct StepSchedule {
+    int64_t B = 0;
+    int step_kernel = 0, dtype_size = 0;
+    std::vector<LaunchGroup> groups;
+    TileItem* d_items = nullptr;
+};
 
 struct GraphEntry {
     int64_t B;
@@ -366,8 +437,11 @@ struct pgx_plan {
     int fused_warps = 0;  // 0 = auto
     int use_graph = 1;    // stepwise: replay the step sequence as a CUDA graph
     std::vector<GraphEntry> graphs;
+    std::vector<StepSchedule> schedules;
     cudaStream_t cap_stream = nullptr;
     int last_graph = 0;
+    int batch_levels = 1; // share one launch among the tile-eligible steps of a dependency level
+    cudaEvent_t* prof_events = nullptr;  // set only inside pgx_profile_steps
     int step_kernel = 0;  // 0 = auto (tile-cooperative where possible), 1 = generic per-thread kernel only
     int fused_kernel = 0; // 0 = auto, 1 = generic (v1), 2 = table-driven/shared workspace, 3 = table-driven/global workspace
     int last_variant = 0;
@@ -491,7 +565,7 @@ int pgx_plan_create(const pgx_plan_desc* desc, pgx_plan** out) {
                     return bad(PGX_ERR_BOUNDS, "step output overlaps one of its operands");
             }
         }
-        pl->steps.push_back(StepInfo{(int)off, (int)len, out_size, sum_size, K});
+        pl->steps.push_back(StepInfo{(int)off, (int)len, out_size, sum_size, K, r[10]});
         pl->max_joint = std::max(pl->max_joint, out_size * std::max<int64_t>(1, sum_size));
     }
     int64_t out_total = 0;
@@ -534,6 +608,8 @@ void pgx_plan_destroy(pgx_plan* plan) {
     if (plan->d_pool) cudaFree(plan->d_pool);
     if (plan->d_micro) cudaFree(plan->d_micro);
     for (GraphEntry& g : plan->graphs) cudaGraphExecDestroy(g.exec);
+    for (StepSchedule& c : plan->schedules)
+        if (c.d_items) cudaFree(c.d_items);
     if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
     delete plan;
 }
@@ -659,67 +735,123 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
         const int64_t b_tiles = (B + bt - 1) / bt;
         if (b_tiles > 65535) return fail(PGX_ERR_UNSUPPORTED, "batch too large for one stepwise launch (max 2,097,120)");
         const int per_block = 256 >> bt_log2;
-        auto enqueue = [&](cudaStream_t qs) -> int {
-            int64_t n = 0;
-            int64_t& launches = n;
-        for (const StepInfo& s : pl->steps) {
-                // tile-cooperative kernel when the summed range's offset table fits shared memory
+        // launch schedule for this batch size: tile-eligible steps of one dependency level share a launch
+        StepSchedule* sched = nullptr;
+        for (StepSchedule& c : pl->schedules)
+            if (c.B == B && c.step_kernel == pl->step_kernel + 2 * pl->batch_levels && c.dtype_size == (int)sizeof(T)) sched = &c;
+        if (!sched) {
+            StepSchedule ns;
+            ns.B = B;
+            ns.step_kernel = pl->step_kernel + 2 * pl->batch_levels;
+            ns.dtype_size = (int)sizeof(T);
+            std::vector<TileItem> items;
+            const int o_per_warp = 32 >> bt_log2;
+            auto flush = [&](LaunchGroup& g) {
+                if (g.n_items > 0) ns.groups.push_back(g);
+                g = LaunchGroup();
+            };
+            LaunchGroup cur;
+            int cur_level = -1;
+            for (size_t si = 0; si < pl->steps.size(); ++si) {
+                const StepInfo& s = pl->steps[si];
                 const int64_t stab_words = s.sum_size * s.n_ops;
-                if (s.n_ops <= 8 && stab_words <= 8192 && pl->step_kernel != 1) {
-                    const int o_per_warp = 32 >> bt_log2;
-                    int btb = (int)(b_tiles < 4 ? b_tiles : 4);
-                    const int64_t b_blocks = (b_tiles + btb - 1) / btb;
-                    int64_t TO = (s.out_size * b_blocks) / (148 * 4);  // aim at >= 4 CTAs per SM when there is work
-                    TO = TO < 8 * o_per_warp ? 8 * o_per_warp : (TO > 512 ? 512 : TO);
-                    if (TO * s.n_ops > 2048) TO = 2048 / s.n_ops;
-                    TO = (TO + o_per_warp - 1) / o_per_warp * o_per_warp;
-                    if (TO > s.out_size) TO = (s.out_size + o_per_warp - 1) / o_per_warp * o_per_warp;
-                    dim3 grid((unsigned)((s.out_size + TO - 1) / TO), (unsigned)b_blocks);
-                    const size_t smem = (size_t)(((s.rec_len + 3) & ~3) + TO * s.n_ops + stab_words) * sizeof(int32_t);
-#define PGX_LAUNCH_TILE(MK)                                                                                          \
-    k_contract_tile<T, MK><<<grid, 256, smem, qs>>>(pl->d_pool, s.rec_off, s.rec_len, pl->ev_card_off, cst, ws, ev, \
-                                                        pl->n_ev, B, ldb, bt_log2, (int)TO, btb)
+                const bool tile_ok = s.n_ops <= 8 && stab_words <= 8192 && pl->step_kernel != 1;
+                if (!tile_ok || s.level != cur_level || !pl->batch_levels) flush(cur);
+                cur_level = s.level;
+                if (!tile_ok) {
+                    LaunchGroup g;
+                    g.generic_step = (int)si;
+                    g.n_items = 1;
+                    ns.groups.push_back(g);
+                    continue;
+                }
+                int btb = (int)(b_tiles < 4 ? b_tiles : 4);
+                int64_t b_blocks = (b_tiles + btb - 1) / btb;
+                int64_t TO = (s.out_size * b_blocks) / (148 * 4);  // aim at >= 4 CTAs per SM when there is work
+                if (TO < 8 * o_per_warp) {
+                    // little work along the output: one evidence tile per CTA, one entry per warp
+                    btb = 1;
+                    b_blocks = b_tiles;
+                    TO = 8 * o_per_warp;
+                }
+                if (TO > 512) TO = 512;
+                if (TO * s.n_ops > 2048) TO = 2048 / s.n_ops;
+                TO = (TO + o_per_warp - 1) / o_per_warp * o_per_warp;
+                if (TO > s.out_size) TO = (s.out_size + o_per_warp - 1) / o_per_warp * o_per_warp;
+                const int64_t n_blocks = ((s.out_size + TO - 1) / TO) * b_blocks;
+                if (cur.n_items > 0 && (int64_t)cur.n_blocks + n_blocks > (1LL << 30)) flush(cur);
+                if (cur.n_items == 0) cur.first_item = (int)items.size();
+                items.push_back(TileItem{s.rec_off, s.rec_len, (int32_t)TO, btb, (int32_t)b_blocks, (int32_t)cur.n_blocks});
+                cur.n_items += 1;
+                cur.n_blocks += (int)n_blocks;
+                cur.max_k = std::max(cur.max_k, s.n_ops);
+                cur.smem = std::max(cur.smem, (size_t)(((s.rec_len + 3) & ~3) + TO * s.n_ops + stab_words) * sizeof(int32_t));
+            }
+            flush(cur);
+            if (!items.empty()) {
+                PGX_CUDA(cudaMalloc((void**)&ns.d_items, items.size() * sizeof(TileItem)));
+                PGX_CUDA(cudaMemcpy(ns.d_items, items.data(), items.size() * sizeof(TileItem), cudaMemcpyHostToDevice));
+            }
+            if (pl->schedules.size() >= 8) {
+                if (pl->schedules.front().d_items) cudaFree(pl->schedules.front().d_items);
+                pl->schedules.erase(pl->schedules.begin());
+                for (GraphEntry& g : pl->graphs) cudaGraphExecDestroy(g.exec);  // graphs reference the item tables
+                pl->graphs.clear();
+            }
+            pl->schedules.push_back(ns);
+            sched = &pl->schedules.back();
+        }
+        auto enqueue = [&](cudaStream_t qs) -> int {
+            int n = 0;
+            cudaEvent_t* evs = pl->prof_events;
+            int ev_idx = 0;
+            for (const LaunchGroup& g : sched->groups) {
+                if (g.generic_step >= 0) {
+                    const StepInfo& s = pl->steps[g.generic_step];
+                    // generic kernel: consecutive entries per thread, as many as leave >= ~4 waves of CTAs on 148 SMs
+                    int64_t opt = (s.out_size * b_tiles) / (per_block * 148LL * 8 * 4);
+                    opt = opt < 1 ? 1 : (opt > 16 ? 16 : opt);
+                    const int64_t runs = (s.out_size + opt - 1) / opt;
+                    dim3 grid((unsigned)((runs + per_block - 1) / per_block), (unsigned)b_tiles);
+                    const size_t smem = (size_t)s.rec_len * sizeof(int32_t);
+#define PGX_LAUNCH_STEP(MK)                                                                                      \
+    k_contract_step<T, MK><<<grid, 256, smem, qs>>>(pl->d_pool, s.rec_off, s.rec_len, pl->ev_card_off, cst, ws, ev, \
+                                                    pl->n_ev, B, ldb, bt_log2, (int)opt)
                     if (s.n_ops <= 2)
-                        PGX_LAUNCH_TILE(2);
+                        PGX_LAUNCH_STEP(2);
                     else if (s.n_ops <= 4)
+                        PGX_LAUNCH_STEP(4);
+                    else if (s.n_ops <= 8)
+                        PGX_LAUNCH_STEP(8);
+                    else
+                        PGX_LAUNCH_STEP(MAX_OPS);
+#undef PGX_LAUNCH_STEP
+                } else {
+                    const TileItem* d_it = sched->d_items + g.first_item;
+#define PGX_LAUNCH_TILE(MK)                                                                                           \
+    k_contract_tile<T, MK><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off, cst, \
+                                                                      ws, ws, ev, pl->n_ev, B, ldb, bt_log2)
+                    if (g.max_k <= 2)
+                        PGX_LAUNCH_TILE(2);
+                    else if (g.max_k <= 4)
                         PGX_LAUNCH_TILE(4);
                     else
                         PGX_LAUNCH_TILE(8);
 #undef PGX_LAUNCH_TILE
-                    ++launches;
-                    continue;
                 }
-                // generic kernel: consecutive entries per thread, as many as leave >= ~4 waves of CTAs on 148 SMs
-                int64_t opt = (s.out_size * b_tiles) / (per_block * 148LL * 8 * 4);
-                opt = opt < 1 ? 1 : (opt > 16 ? 16 : opt);
-                const int64_t runs = (s.out_size + opt - 1) / opt;
-                dim3 grid((unsigned)((runs + per_block - 1) / per_block), (unsigned)b_tiles);
-                const size_t smem = (size_t)s.rec_len * sizeof(int32_t);
-#define PGX_LAUNCH_STEP(MK)                                                                                      \
-    k_contract_step<T, MK><<<grid, 256, smem, qs>>>(pl->d_pool, s.rec_off, s.rec_len, pl->ev_card_off, cst, ws, ev, \
-                                                        pl->n_ev, B, ldb, bt_log2, (int)opt)
-                if (s.n_ops <= 2)
-                    PGX_LAUNCH_STEP(2);
-                else if (s.n_ops <= 4)
-                    PGX_LAUNCH_STEP(4);
-                else if (s.n_ops <= 8)
-                    PGX_LAUNCH_STEP(8);
-                else
-                    PGX_LAUNCH_STEP(MAX_OPS);
-#undef PGX_LAUNCH_STEP
-                ++launches;
+                ++n;
+                if (evs) cudaEventRecord(evs[++ev_idx], qs);
             }
             if (pl->n_segs > 0) {
                 dim3 grid((unsigned)((B + 127) / 128), (unsigned)pl->n_segs);
-                if (pl->n_segs > 65535) return fail(PGX_ERR_UNSUPPORTED, "too many output segments");
                 k_emit<T><<<grid, 128, 0, qs>>>(pl->d_pool, pl->segs_off, ws, out, pl->out_elems, B, ldb);
-                ++launches;
+                ++n;
             }
-            return (int)n;
+            return n;
         };
         if (pl->n_segs > 65535) return fail(PGX_ERR_UNSUPPORTED, "too many output segments");
         bool replayed = false;
-        if (pl->use_graph && pl->n_steps >= 8) {
+        if (pl->use_graph && pl->n_steps >= 8 && !pl->prof_events) {
             // replay the launch sequence as a CUDA graph (captured once per argument tuple)
             GraphEntry* hit = nullptr;
             for (GraphEntry& g : pl->graphs)
@@ -780,6 +912,30 @@ int pgx_run_batch(pgx_plan* plan, const int32_t* ev_states, void* out, void* wor
     cudaStream_t st = (cudaStream_t)stream;
     if (plan->dtype == PGX_F64) return run_typed<double>(plan, ev_states, out, workspace, B, st);
     return run_typed<float>(plan, ev_states, out, workspace, B, st);
+}
+
+int pgx_profile_steps(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
+                      int64_t B, void* stream, float* step_ms, int32_t n_steps) {
+    if (!plan || !step_ms) return fail(PGX_ERR_INVALID, "null argument");
+    if (n_steps < plan->n_steps) return fail(PGX_ERR_INVALID, "step_ms too short");
+    const int saved_mode = plan->mode;
+    std::vector<cudaEvent_t> evs(plan->n_steps + 1);
+    for (auto& e : evs) PGX_CUDA(cudaEventCreate(&e));
+    plan->mode = PGX_MODE_STEPWISE;
+    const int saved_batch = plan->batch_levels;
+    plan->batch_levels = 0;  // one launch per step so that every step gets its own event pair
+    plan->prof_events = evs.data();
+    PGX_CUDA(cudaEventRecord(evs[0], (cudaStream_t)stream));
+    const int rc = pgx_run_batch(plan, ev_states, out, workspace, workspace_bytes, B, stream);
+    plan->prof_events = nullptr;
+    plan->mode = saved_mode;
+    plan->batch_levels = saved_batch;
+    if (rc == PGX_OK) {
+        PGX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        for (int i = 0; i < plan->n_steps; ++i) PGX_CUDA(cudaEventElapsedTime(&step_ms[i], evs[i], evs[i + 1]));
+    }
+    for (auto& e : evs) cudaEventDestroy(e);
+    return rc;
 }
 
 int pgx_evidence_reduce(int32_t dtype, const void* table, int64_t table_entries, int32_t n_free,

@@ -146,6 +146,31 @@ class CompiledPlan:
             )
         return out
 
+    def profile_steps(self, ev_states):
+        """Per-step device time (ms) of one stepwise pass: list of (ms, out_size, sum_size, n_operands, alg_bytes)."""
+        torch = _torch()
+        B = ev_states.shape[0]
+        out = torch.empty((B, self.out_elems), dtype=self.torch_dtype, device=self.device)
+        need = self.workspace_bytes(B)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        n = self.plan.n_steps
+        ms = (C.c_float * n)()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        N.check(self.lib.pgx_profile_steps(self.handle, C.c_void_p(ev_states.data_ptr() if self.n_ev else 0),
+                                           C.c_void_p(out.data_ptr()), C.c_void_p(self._ws.data_ptr()), self._ws.numel(), B,
+                                           C.c_void_p(stream), ms, n))
+        item = 8 if self.dtype_name == "float64" else 4
+        rows = []
+        for t, st in zip(ms, self.plan.steps):
+            ssz = 1
+            for v in st.sum_vars:
+                ssz *= self.plan.card[v]
+            work = st.out.size + sum(tb.size for tb, _ in st.operands if tb.kind == 1)
+            const = sum(tb.size for tb, _ in st.operands if tb.kind == 0)
+            rows.append((float(t), st.out.size, ssz, len(st.operands), item * (B * work + const), st.level))
+        return rows
+
     def run_pinned(self, ev_pinned, out_pinned, n_chunks: int = 0, n_streams: int = 3):
         """End-to-end call with HOST buffers: pinned int32 [B, n_ev] in, pinned [B, out_elems] out.
 
