@@ -302,6 +302,7 @@ class PlanBuilder:
                                             split=False)
                     return self.contract([partial], out_vars, divisors=divisors, reduce_max=reduce_max, level=level,
                                          optimize=False, split=False)
+        ops.sort(key=lambda t: t.kind)  # batch-invariant operands first (the fused kernel specialises on that)
         out = self.new_work(out_vars)
         idx = len(self.steps)
         self.steps.append(

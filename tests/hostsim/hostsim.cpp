@@ -69,8 +69,8 @@ extern "C" int hostsim_micro_f64(const int32_t* pool, const double* cst, const i
     const int32_t* items = mp.data() + mp[3];
     for (int lv = 0; lv < mp[0]; ++lv) {
         for (int i = levels[lv]; i < levels[lv + 1]; ++i) {
-            const int32_t* sr = mp.data() + items[2 * i];
-            const int o = items[2 * i + 1];
+            const int32_t* sr = mp.data() + items[ITEM_WORDS * i];
+            for (int o = items[ITEM_WORDS * i + 1]; o < items[ITEM_WORDS * i + 1] + items[ITEM_WORDS * i + 2]; ++o) {
             const int K = sr[0], n_mul = sr[1], flags = sr[2], sum_size = sr[3], out_off = sr[4];
             const int32_t* ot = mp.data() + sr[5] + o * K;
             const int32_t* st = mp.data() + sr[6];
@@ -104,6 +104,7 @@ extern "C" int hostsim_micro_f64(const int32_t* pool, const double* cst, const i
                     acc = (r != r) ? 0.0 : r;
                 }
                 ws[(int64_t)(out_off + o) * ldb + b] = acc;
+            }
             }
         }
     }
