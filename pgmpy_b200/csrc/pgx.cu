@@ -688,23 +688,33 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
         int G = pl->fused_warps;
         if (G <= 0) {
             if (smem) {
-                const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (228 * 1024) / (dyn + 1024)));
-                G = (24 + per_sm - 1) / per_sm;  // ~24 warps per SM
+                // CTAs per SM by shared memory, warps per SM by registers (64 regs fast-only, ~96 otherwise)
+                const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (dyn + 1024)));
+                const int warps_per_sm = pl->micro.all_fast ? 32 : 20;
+                G = warps_per_sm / per_sm;
                 if (G < 4) G = 4;
             } else {
                 G = (int)((148 * 16 + rows - 1) / rows);
+                if (G < 4) G = 4;
             }
         }
         if (G < 1) G = 1;
         if (G > 16) G = 16;
-        if (smem) {
-            PGX_CUDA(cudaFuncSetAttribute(k_plan_fused2<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            k_plan_fused2<T, true><<<(unsigned)rows, 32 * G, dyn, st>>>(pl->d_micro, cst, ws, ev, pl->d_pool + pl->ev_card_off,
-                                                                      out, pl->n_ev, (int)pl->ws_entries, B, ldb);
+#define PGX_LAUNCH_FUSED2(SM, FO)                                                                                     \
+    k_plan_fused2<T, SM, FO><<<(unsigned)rows, 32 * G, dyn, st>>>(pl->d_micro, cst, ws, ev, pl->d_pool + pl->ev_card_off, out, \
+                                                                  pl->n_ev, (int)pl->ws_entries, B, ldb)
+        if (smem && pl->micro.all_fast) {
+            PGX_CUDA(cudaFuncSetAttribute(k_plan_fused2<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            PGX_LAUNCH_FUSED2(true, true);
+        } else if (smem) {
+            PGX_CUDA(cudaFuncSetAttribute(k_plan_fused2<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            PGX_LAUNCH_FUSED2(true, false);
+        } else if (pl->micro.all_fast) {
+            PGX_LAUNCH_FUSED2(false, true);
         } else {
-            k_plan_fused2<T, false><<<(unsigned)rows, 32 * G, dyn, st>>>(pl->d_micro, cst, ws, ev, pl->d_pool + pl->ev_card_off,
-                                                                       out, pl->n_ev, (int)pl->ws_entries, B, ldb);
+            PGX_LAUNCH_FUSED2(false, false);
         }
+#undef PGX_LAUNCH_FUSED2
         PGX_CUDA(cudaGetLastError());
         launches = 1;
         pl->last_variant = smem ? 2 : 3;

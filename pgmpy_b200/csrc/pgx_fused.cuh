@@ -39,6 +39,7 @@ struct MicroInfo {
     int n_items = 0;
     int max_k = 0;
     int64_t words = 0;
+    bool all_fast = false;  // every step has a fast code
 };
 
 // Host: expand the packed plan into the microprogram. Returns false when the plan is too large for tables.
@@ -74,6 +75,7 @@ inline bool build_micro(const int32_t* pool, std::vector<int32_t>& w, MicroInfo&
     std::vector<int32_t> level_first(n_levels + 1, 0);
     int cur_level = 0;
     int max_k = 0;
+    bool all_fast = true;
     for (int s = 0; s < n_steps; ++s) {
         const int32_t* r = pool + index[s];
         const int A = r[0], S = r[1], K = r[2], flags = r[3], level = r[10];
@@ -107,7 +109,8 @@ inline bool build_micro(const int32_t* pool, std::vector<int32_t>& w, MicroInfo&
         }
         w[srec + 7] = wsmask;
         w[srec + 8] = evmask;
-        w[srec + 9] = (flags == 0 && const_first && K <= 5) ? K * 8 + n_const : -1;
+        w[srec + 9] = (flags == 0 && const_first && (K <= 4 || (K == 5 && n_const <= 2))) ? K * 8 + n_const : -1;
+        if (w[srec + 9] < 0) all_fast = false;
         // otab[o][k]
         const int otab = (int)w.size();
         w[srec + 5] = otab;
@@ -194,6 +197,7 @@ inline bool build_micro(const int32_t* pool, std::vector<int32_t>& w, MicroInfo&
     info.n_items = (int)(items.size() / ITEM_WORDS);
     info.max_k = max_k;
     info.words = (int64_t)w.size();
+    info.all_fast = all_fast;
     return true;
 }
 
@@ -319,8 +323,10 @@ __device__ __forceinline__ void micro_chunk(const int32_t* __restrict__ mp, cons
 }
 
 // blockDim.x = 32 * G. Shared memory: [ws_entries][32] T (SMEM only), then evidence [n_ev][32] int32.
-template <typename T, bool SMEM>
-__global__ void __launch_bounds__(512, 1) k_plan_fused2(const int32_t* __restrict__ mp, const T* __restrict__ cst,
+// FAST_ONLY: every step of the plan has a fast code (plain sum-product, const operands first, <= 5 operands), so the
+// general chunk function is not compiled in — fewer registers, two 512-thread CTAs per SM.
+template <typename T, bool SMEM, bool FAST_ONLY>
+__global__ void __launch_bounds__(512, FAST_ONLY ? 2 : 1) k_plan_fused2(const int32_t* __restrict__ mp, const T* __restrict__ cst,
                                                      T* __restrict__ ws_g, const int32_t* __restrict__ ev,
                                                      const int32_t* __restrict__ ev_card, T* __restrict__ out, int n_ev,
                                                      int ws_entries, int64_t B, int64_t ldb) {
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(512, 1) k_plan_fused2(const int32_t* __restric
                     PGX_FAST(4, 0) PGX_FAST(4, 1) PGX_FAST(4, 2) PGX_FAST(4, 3) PGX_FAST(4, 4)
                     PGX_FAST(5, 0) PGX_FAST(5, 1) PGX_FAST(5, 2)
                     default:
-                        switch (__ldg(sr)) {
+                        if (!FAST_ONLY) switch (__ldg(sr)) {
                             case 1: micro_chunk<T, 1, SMEM>(mp, sr, o0, n_o, cst, wsb, ldb, evs, lane); break;
                             case 2: micro_chunk<T, 2, SMEM>(mp, sr, o0, n_o, cst, wsb, ldb, evs, lane); break;
                             case 3: micro_chunk<T, 3, SMEM>(mp, sr, o0, n_o, cst, wsb, ldb, evs, lane); break;

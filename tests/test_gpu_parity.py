@@ -257,8 +257,9 @@ def test_full_size_batch_properties(torch_cuda):
     ev = torch.from_numpy(states).cuda()
     out = cp.run(ev).clone()
     assert cp.last_variant == "tables-smem"
+    # other kernels contract multiply-adds differently (FMA): equal to ~1 ulp-scale, not bit for bit
     cp.set_mode("fused", 0, "generic")
-    assert torch.equal(cp.run(ev), out)
+    assert float(((cp.run(ev) - out).abs() / out.abs().clamp_min(1e-300)).max()) <= 1e-13
     cp.set_mode("fused")
     for seg in cp.plan.segments:
         s = out[:, seg.out_offset : seg.out_offset + seg.table.size].sum(dim=1)
@@ -268,7 +269,7 @@ def test_full_size_batch_properties(torch_cuda):
     assert torch.equal(out_p, out[perm])
     cp.set_mode("stepwise")
     out_s = cp.run(ev)
-    assert torch.equal(out_s, out)
+    assert float(((out_s - out).abs() / out.abs().clamp_min(1e-300)).max()) <= 1e-13
     # spot-check 64 rows against the oracle interpreter
     idx = np.linspace(0, B - 1, 64).astype(int)
     want = run_plan(cp.plan.pool, cp.plan.const_blob, states[idx])
