@@ -48,3 +48,50 @@ def gather_posteriors(local, total_rows: int = None, group=None):
     if total_rows is not None and out.shape[0] != total_rows:
         raise RuntimeError("gathered row count does not match the batch")
     return out
+
+
+def bind_process_to_gpu_numa(device_index: int):
+    """Pin this process to the CPUs local to its GPU (PCIe root / NUMA node) so that pinned host buffers are
+    first-touched on the right node; with 8 ranks streaming posteriors back to the host this decides whether the
+    D2H copies fight over one socket. Returns the CPU list used, or None when the topology cannot be read."""
+    import os
+
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        handle = None
+        for i in range(pynvml.nvmlDeviceGetCount()):
+            h = pynvml.nvmlDeviceGetHandleByIndex(i)
+            u = pynvml.nvmlDeviceGetUUID(h)
+            u = u.decode() if isinstance(u, bytes) else u
+            if uuid in u or u.replace("GPU-", "") == uuid:
+                handle = h
+                break
+        if handle is None:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(handle).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # nvml pads the domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        path = f"/sys/bus/pci/devices/{bus}/local_cpulist"
+        with open(path) as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return text
+    except Exception:
+        return None
