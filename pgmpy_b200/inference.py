@@ -199,6 +199,27 @@ class VariableElimination(_Inference):
         cp = self._plan(list(variables), list(evidence_vars), joint, elimination_order)
         return self._run(cp, evidence_states)
 
+    def query_batch_mixed(self, variables, evidence_rows, joint=True):
+        """Mixed-evidence batch: `evidence_rows` is a list of {var: state name} dicts whose observed SETS may
+        differ from row to row (what DiscreteBayesianNetwork.predict_probability feeds the reference one row at a
+        time, pgmpy/models/DiscreteBayesianNetwork.py:973-989). Rows are bucketed by evidence-variable signature,
+        every bucket runs as one batched plan, results come back in row order as a CUDA tensor [B, out_elems]."""
+        torch = require_cuda()
+        buckets: Dict[tuple, List[int]] = {}
+        for i, row in enumerate(evidence_rows):
+            buckets.setdefault(tuple(sorted(row, key=str)), []).append(i)
+        out = None
+        for sig, idx in buckets.items():
+            ev_vars = list(sig)
+            self._check_query(variables, {v: None for v in ev_vars})
+            cp = self._plan(list(variables), ev_vars, joint, None)
+            states = self._states_of(ev_vars, [evidence_rows[i] for i in idx])
+            res = self._run(cp, states)
+            if out is None:
+                out = torch.empty((len(evidence_rows), res.shape[1]), dtype=res.dtype, device=res.device)
+            out[torch.as_tensor(idx, device=res.device)] = res
+        return out
+
     def induced_width(self, elimination_order):
         raise NotImplementedError("induced_width is outside the accelerated path")
 

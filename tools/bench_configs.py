@@ -1,0 +1,117 @@
+"""Runs the BASELINE.json configurations other than the headline one and prints one JSON line each
+(device-resident throughput, CUDA events; parity of these paths is asserted in tests/test_gpu_parity.py).
+
+    python tools/bench_configs.py [alarm_ve] [mixed_ve] [large] [munin]
+"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import pgmpy_b200 as px
+from pgmpy_b200.evidence import sample_evidence
+from pgmpy_b200.inference import BeliefPropagation, VariableElimination
+
+PEAK = 6544.7
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timed(fn, warm=2, reps=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def alarm_ve(batch=1024):
+    """configs[0]: alarm, VariableElimination.query all-variable marginals over 1024 evidence sets, fp64."""
+    m = px.get_example_model("alarm")
+    ve = VariableElimination(m)
+    ev_vars, states = sample_evidence(m, batch, 5, seed=1)
+    ev = torch.from_numpy(states).cuda()
+    free = [v for v in m.nodes() if v not in ev_vars]
+    t0 = time.perf_counter()
+    plans = [ve._plan([q], ev_vars, True, None) for q in free]
+    compile_s = time.perf_counter() - t0
+    outs = [torch.empty((batch, cp.out_elems), dtype=torch.float64, device="cuda") for cp in plans]
+
+    def run():
+        for cp, o in zip(plans, outs):
+            cp.run(ev, out=o)
+
+    ms = timed(run)
+    alg = sum(cp.plan.algorithmic_bytes(batch) for cp in plans)
+    print(json.dumps({"config": "alarm VE all-variable marginals (one pruned plan per query variable)", "batch": batch,
+                      "plans": len(plans), "plan_compile_s": round(compile_s, 2), "ms_per_batch": ms,
+                      "evidence_queries_per_sec": batch / ms * 1e3, "single_variable_queries_per_sec": batch * len(plans) / ms * 1e3,
+                      "alg_GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / PEAK}), flush=True)
+
+
+def mixed_ve(name, batch=262144, n_sig=16):
+    """configs[2]: hepar2 / win95pts VE (min-fill order), mixed evidence: 16 observed sets per batch, equal shares."""
+    m = px.get_example_model(name)
+    ve = VariableElimination(m)
+    nodes = sorted(m.nodes())
+    per = batch // n_sig
+    rng = np.random.default_rng(7)
+    q = nodes[len(nodes) // 2]
+    jobs = []
+    t0 = time.perf_counter()
+    for sgn in range(n_sig):
+        cand = [v for v in nodes if v != q]
+        ev_vars = [cand[i] for i in rng.choice(len(cand), 8, replace=False)]
+        _, states = sample_evidence(m, per, 8, seed=100 + sgn, evidence_vars=ev_vars)
+        cp = ve._plan([q], ev_vars, True, None)
+        jobs.append((cp, torch.from_numpy(states).cuda(), torch.empty((per, cp.out_elems), dtype=torch.float64, device="cuda")))
+    compile_s = time.perf_counter() - t0
+
+    def run():
+        for cp, ev, o in jobs:
+            cp.run(ev, out=o)
+
+    ms = timed(run)
+    alg = sum(cp.plan.algorithmic_bytes(per) for cp, _, _ in jobs)
+    print(json.dumps({"config": f"{name} VE single-variable posterior, mixed evidence ({n_sig} signatures x {per} sets)", "batch": per * n_sig,
+                      "plan_compile_s": round(compile_s, 2), "ms_per_batch": ms, "evidence_queries_per_sec": per * n_sig / ms * 1e3,
+                      "alg_GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / PEAK}), flush=True)
+
+
+def bp_all_marginals(name, batch, k=8, reps=3):
+    """configs[3]/[4]: large-table junction-tree all-marginals (pathfinder, diabetes, munin)."""
+    m = px.get_example_model(name)
+    bp = BeliefPropagation(m)
+    ev_vars, states = sample_evidence(m, batch, k, seed=1)
+    t0 = time.perf_counter()
+    cp = bp.marginals_plan(ev_vars)
+    compile_s = time.perf_counter() - t0
+    ev = torch.from_numpy(states).cuda()
+    out = torch.empty((batch, cp.out_elems), dtype=torch.float64, device="cuda")
+    ms = timed(lambda: cp.run(ev, out=out), warm=2, reps=reps)
+    alg = cp.plan.algorithmic_bytes(batch)
+    print(json.dumps({"config": f"{name} junction-tree all-variable marginals", "batch": batch, "mode": cp.last_mode, "variant": cp.last_variant,
+                      "launches": cp.last_launches, "steps": cp.plan.n_steps, "plan_compile_s": round(compile_s, 2), "ms_per_batch": ms,
+                      "evidence_queries_per_sec": batch / ms * 1e3, "alg_bytes_per_evidence_set": alg / batch,
+                      "alg_GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / PEAK,
+                      "workspace_GB": cp.workspace_bytes(batch) / 1e9}), flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["alarm_ve", "mixed_ve", "large", "munin"]
+    if "alarm_ve" in what:
+        alarm_ve()
+    if "mixed_ve" in what:
+        mixed_ve("hepar2")
+        mixed_ve("win95pts")
+    if "large" in what:
+        bp_all_marginals("pathfinder", 16384)
+        bp_all_marginals("diabetes", 2048)
+    if "munin" in what:
+        for b in (64, 256, 1024):
+            bp_all_marginals("munin", b)
