@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -579,7 +580,11 @@ int pgx_plan_create(const pgx_plan_desc* desc, pgx_plan** out) {
     (void)out_total;
     pl->pool.assign(p, p + W);
     std::vector<int32_t> micro_words;
-    if (pl->n_steps > 0 && pl->max_joint <= (1 << 16)) build_micro(p, micro_words, pl->micro);
+    if (pl->n_steps > 0 && pl->max_joint <= (1 << 16)) {
+        int cpl = 48;
+        if (const char* e = std::getenv("PGX_CHUNKS_PER_LEVEL")) cpl = std::max(1, std::atoi(e));  // tuning knob
+        build_micro(p, micro_words, pl->micro, 1 << 21, cpl);
+    }
     cudaError_t e = cudaGetDevice(&pl->device);
     if (e != cudaSuccess) return bad(PGX_ERR_CUDA, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
     e = cudaMalloc((void**)&pl->d_pool, (size_t)W * sizeof(int32_t));

@@ -104,10 +104,25 @@ class CompiledPlan:
         return int(self.lib.pgx_workspace_bytes(self.handle, batch))
 
     # ---- execution ---------------------------------------------------------------------------
+    # Largest workspace a single launch sequence may ask for; bigger batches are processed in row tiles
+    # (munin needs 169 MB of work tables per evidence set: 1024 sets would want 173 GB at once).
+    MAX_WORKSPACE_BYTES = 32 << 30
+
     def run(self, ev_states, out=None, workspace=None):
         """ev_states: int32 CUDA tensor [B, n_ev] (or [B, 0] / None with B given by `out`).
         Returns out: [B, out_elems] CUDA tensor of the plan dtype. Asynchronous on the current stream."""
         torch = _torch()
+        if workspace is None:
+            B_all = ev_states.shape[0] if ev_states is not None else (out.shape[0] if out is not None else 0)
+            if B_all > 32 and self.workspace_bytes(B_all) > self.MAX_WORKSPACE_BYTES:
+                per_set = self.workspace_bytes(32) // 32
+                tile = max(32, int(self.MAX_WORKSPACE_BYTES // max(per_set, 1)) // 32 * 32)
+                if out is None:
+                    out = torch.empty((B_all, self.out_elems), dtype=self.torch_dtype, device=self.device)
+                for lo in range(0, B_all, tile):
+                    hi = min(B_all, lo + tile)
+                    self.run(None if ev_states is None else ev_states[lo:hi], out=out[lo:hi])
+                return out
         if ev_states is None:
             if out is None:
                 raise ValueError("batch size unknown: pass ev_states or out")

@@ -412,3 +412,18 @@ def test_mixed_evidence_batch_matches_per_row_queries(torch_cuda):
     out = ve.query_batch_mixed(["HRBP"], rows).cpu().numpy()
     for i, row in enumerate(rows):
         assert rel_err(out[i], O.ve_query(net, ["HRBP"], row).values) <= 1e-12
+
+
+def test_batch_is_tiled_when_the_workspace_would_be_too_large(torch_cuda):
+    """Row tiling inside CompiledPlan.run gives the same result as one pass."""
+    torch = torch_cuda
+    m = px.get_example_model("hepar2")
+    ev_vars, states = sample_evidence(m, 300, 8, seed=5)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars)
+    cp = _engine()(plan)
+    cp.set_mode("stepwise")
+    ev = torch.from_numpy(states).cuda()
+    whole = cp.run(ev).clone()
+    cp.MAX_WORKSPACE_BYTES = cp.workspace_bytes(64)
+    tiled = cp.run(ev)
+    assert torch.equal(tiled, whole)
