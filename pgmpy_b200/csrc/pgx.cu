@@ -581,7 +581,7 @@ int pgx_plan_create(const pgx_plan_desc* desc, pgx_plan** out) {
     pl->pool.assign(p, p + W);
     std::vector<int32_t> micro_words;
     if (pl->n_steps > 0 && pl->max_joint <= (1 << 16)) {
-        int cpl = 48;
+        int cpl = 16;  // ~ one chunk per warp of a 16-warp CTA: decode overhead beats perfect balance (measured 12..96)
         if (const char* e = std::getenv("PGX_CHUNKS_PER_LEVEL")) cpl = std::max(1, std::atoi(e));  // tuning knob
         build_micro(p, micro_words, pl->micro, 1 << 21, cpl);
     }

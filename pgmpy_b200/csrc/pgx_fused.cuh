@@ -44,7 +44,7 @@ struct MicroInfo {
 
 // Host: expand the packed plan into the microprogram. Returns false when the plan is too large for tables.
 inline bool build_micro(const int32_t* pool, std::vector<int32_t>& w, MicroInfo& info, int64_t max_words = 1 << 21,
-                        int chunks_per_level = 48) {
+                        int chunks_per_level = 16) {
     const int n_steps = pool[3], n_segs = pool[4], out_elems = pool[5];
     const int32_t* index = pool + pool[10];
     int n_levels = 0;
