@@ -21,6 +21,7 @@
  *                        for B evidence sets at once.
  *   pgx_evidence_reduce  DiscreteFactor.reduce (:535-617) / the greedy-path indexer ExactInference.py:355-365.
  *   pgx_normalize        DiscreteFactor.normalize (:485-533).
+ *   pgx_argmax_rows      compat_fns.argmax over the joint in map_query (inference/ExactInference.py:611).
  *
  * Conventions: plain pointers and sizes only; 0 = success, negative = error (pgx_last_error() gives the
  * text, thread local); no exceptions cross the boundary. The CALLER owns every device buffer
@@ -121,6 +122,10 @@ int pgx_evidence_reduce(int32_t dtype, const void* table, int64_t table_entries,
 /* Stand-alone batched normalise: out[b, i] = src[i, b] / sum_i src[i, b]  (src layout [n][ldb]). */
 int pgx_normalize(int32_t dtype, const void* src, int64_t n, int64_t ldb, void* out, int64_t out_row_len, int64_t B,
                   void* stream);
+
+/* Row-wise argmax of a [B, n] row-major table (first maximum, like numpy.argmax): the decode step of map_query
+ * (pgmpy/inference/ExactInference.py:611-612: argmax over the joint, then DiscreteFactor.assignment). */
+int pgx_argmax_rows(int32_t dtype, const void* src, int64_t n, int64_t B, int32_t* out, void* stream);
 
 /* Leading dimension (in evidence sets) of workspace tables for a batch of B. */
 int64_t pgx_batch_ld(int64_t B);

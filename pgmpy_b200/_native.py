@@ -24,6 +24,7 @@ EXPORTS = (
     "pgx_plan_get_info",
     "pgx_evidence_reduce",
     "pgx_normalize",
+    "pgx_argmax_rows",
     "pgx_batch_ld",
     "pgx_last_error",
     "pgx_abi_version",
@@ -85,6 +86,8 @@ def load():
     lib.pgx_evidence_reduce.restype = C.c_int
     lib.pgx_normalize.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     lib.pgx_normalize.restype = C.c_int
+    lib.pgx_argmax_rows.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.pgx_argmax_rows.restype = C.c_int
     lib.pgx_batch_ld.argtypes = [C.c_int64]
     lib.pgx_batch_ld.restype = C.c_int64
     lib.pgx_last_error.argtypes = []

@@ -368,6 +368,24 @@ __global__ void __launch_bounds__(256) k_evidence_gather(const T* __restrict__ t
     dst[(int64_t)e * ldb + b] = table[off];
 }
 
+// first index of the row maximum (numpy.argmax semantics: first occurrence; NaN propagates like numpy: a NaN wins)
+template <typename T>
+__global__ void __launch_bounds__(128) k_argmax_rows(const T* __restrict__ src, int64_t n, int64_t B, int32_t* __restrict__ out) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const T* row = src + b * n;
+    T best = row[0];
+    int32_t arg = 0;
+    for (int64_t i = 1; i < n; ++i) {
+        const T v = row[i];
+        if (best == best && (v > best || v != v)) {
+            best = v;
+            arg = (int32_t)i;
+        }
+    }
+    out[b] = arg;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128) k_normalize(const T* __restrict__ src, int64_t n, int64_t ldb, T* __restrict__ out,
                                                    int64_t out_row_len, int64_t B) {
@@ -1006,6 +1024,18 @@ int pgx_evidence_reduce(int32_t dtype, const void* table, int64_t table_entries,
                                                        ev_row_len, (float*)dst, n, B, ldb, bt_log2);
     PGX_CUDA(cudaGetLastError());
     PGX_CUDA(cudaFreeAsync(d, st));
+    return PGX_OK;
+}
+
+int pgx_argmax_rows(int32_t dtype, const void* src, int64_t n, int64_t B, int32_t* out, void* stream) {
+    if (!src || !out || n < 1 || B <= 0) return fail(PGX_ERR_INVALID, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((B + 127) / 128);
+    if (dtype == PGX_F64)
+        k_argmax_rows<double><<<grid, 128, 0, st>>>((const double*)src, n, B, out);
+    else
+        k_argmax_rows<float><<<grid, 128, 0, st>>>((const float*)src, n, B, out);
+    PGX_CUDA(cudaGetLastError());
     return PGX_OK;
 }
 

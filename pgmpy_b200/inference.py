@@ -139,20 +139,21 @@ class VariableElimination(_Inference):
             )
         return bn
 
-    def _plan(self, variables, ev_vars, joint, elimination_order, prune=True) -> CompiledPlan:
+    def _plan(self, variables, ev_vars, joint, elimination_order, prune=True, reduce_max=False) -> CompiledPlan:
         order_key = tuple(elimination_order) if isinstance(elimination_order, (list, tuple)) else None
-        key = ("ve", tuple(variables), tuple(ev_vars), joint, order_key, prune)
+        key = ("ve", tuple(variables), tuple(ev_vars), joint, order_key, prune, reduce_max)
         cp = self._plans.get(key)
         if cp is None:
             if isinstance(self.model, JunctionTree):
                 factors = [(tuple(f.variables), f.values, None) for f in self.model.get_factors()]
                 plan = PL.compile_factor_ve_plan(
                     factors, self.cardinality, variables, ev_vars, joint=joint, normalize=True,
-                    elimination_order=order_key,
+                    elimination_order=order_key, reduce_max=reduce_max,
                 )
             else:
                 plan = PL.compile_ve_plan(
-                    self.model, variables, ev_vars, joint=joint, prune=prune, elimination_order=order_key
+                    self.model, variables, ev_vars, joint=joint, prune=prune, elimination_order=order_key,
+                    reduce_max=reduce_max,
                 )
             cp = CompiledPlan(plan, self.dtype)
             self._plans[key] = cp
@@ -220,6 +221,99 @@ class VariableElimination(_Inference):
             out[torch.as_tensor(idx, device=res.device)] = res
         return out
 
+    # ---- max-product queries ---------------------------------------------
+    def _argmax_rows(self, table):
+        """Row-wise argmax on the device (pgx_argmax_rows)."""
+        import ctypes as C
+
+        from . import _native as N
+
+        torch = require_cuda()
+        out = torch.empty((table.shape[0],), dtype=torch.int32, device=table.device)
+        N.check(N.load().pgx_argmax_rows(
+            N.PGX_F64 if table.dtype == torch.float64 else N.PGX_F32, C.c_void_p(table.data_ptr()), table.shape[1],
+            table.shape[0], C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream(table.device).cuda_stream)))
+        return out
+
+    def _decode(self, variables, flat_index) -> dict:
+        """DiscreteFactor.assignment for one flat index of the joint over `variables` (row-major)."""
+        res = {}
+        for v in reversed(list(variables)):
+            c = self.cardinality[v]
+            res[v] = self.states[v][int(flat_index % c)]
+            flat_index //= c
+        return {v: res[v] for v in variables}
+
+    def max_marginal(self, variables=None, evidence=None, elimination_order="MinFill", show_progress=True):
+        """ExactInference.py:459-526: eliminate every other variable with MAX, normalise the table over `variables`
+        (the reference's _variable_elimination normalises joint results of Bayesian networks, :226-229) and return
+        its largest entry. With no `variables` the reference multiplies all factors and takes the maximum of the
+        full joint (:185-190) — the probability of the most probable explanation; we max-eliminate everything."""
+        variables = list(variables) if variables else []
+        evidence = self._check_query(variables, evidence, allow_empty=True)
+        torch = require_cuda()
+        if not variables:
+            # evidence is ignored on this path by the reference (early return before the factors are reduced)
+            nodes = list(self.model.nodes()) if not isinstance(self.model, JunctionTree) else sorted(self.variables, key=str)
+            return float(self._run_unnormalized_max(nodes))
+        ev_vars = list(evidence)
+        cp = self._plan(variables, ev_vars, True, None, reduce_max=True)
+        out = self._run(cp, self._states_of(ev_vars, [evidence]))
+        return float(out.max().item())
+
+    def _run_unnormalized_max(self, nodes):
+        """max over the full joint of prod(all factors) — one max-elimination plan whose last table is emitted raw."""
+        key = ("mpe-value",)
+        cp = self._plans.get(key)
+        if cp is None:
+            if isinstance(self.model, JunctionTree):
+                factors = [(tuple(f.variables), f.values, None) for f in self.model.get_factors()]
+            else:
+                factors = [(tuple(c.variables), c.values, None) for c in self.model.get_cpds()]
+            plan = PL.compile_factor_ve_plan(factors, self.cardinality, [nodes[0]], [], joint=True, normalize=False,
+                                             reduce_max=True)
+            cp = CompiledPlan(plan, self.dtype)
+            self._plans[key] = cp
+        out = self._run(cp, np.zeros((1, 0), dtype=np.int32))
+        return out.max().item()
+
+    def map_query(self, variables=None, evidence=None, virtual_evidence=None, elimination_order="MinFill",
+                  show_progress=True):
+        """ExactInference.py:528-624: sum-product joint over `variables` given the evidence, then the argmax
+        assignment (state names). `variables=None` means every unobserved variable."""
+        evidence = dict(evidence) if evidence is not None else {}
+        if virtual_evidence is not None and isinstance(self.model, DiscreteBayesianNetwork):
+            sub = type(self)(self._virtual(virtual_evidence), dtype=self.dtype)
+            virt = {"__" + str(c.variables[0]): 0 for c in virtual_evidence}
+            return sub.map_query(variables, {**evidence, **virt}, None, elimination_order, show_progress)
+        if not variables:
+            order = list(self.model.nodes()) if not isinstance(self.model, JunctionTree) else sorted(self.variables, key=str)
+            variables = [v for v in order if v not in evidence]
+        variables = list(variables)
+        evidence = self._check_query(variables, evidence)
+        ev_vars = list(evidence)
+        joint = self._joint_for_map(variables, ev_vars, self._states_of(ev_vars, [evidence]))
+        idx = int(self._argmax_rows(joint)[0].item())
+        return self._decode(variables, idx)
+
+    def _joint_for_map(self, variables, ev_vars, states):
+        cp = self._plan(variables, ev_vars, True, None)
+        return self._run(cp, states)
+
+    def map_query_batch(self, variables, evidence_vars, evidence_states):
+        """Batched map_query: int32 CUDA tensor [B, len(variables)] of state indices of the MAP assignment."""
+        torch = require_cuda()
+        variables = list(variables)
+        self._check_query(variables, {v: None for v in evidence_vars})
+        joint = self._joint_for_map(variables, list(evidence_vars), evidence_states)
+        flat = self._argmax_rows(joint).to(torch.int64)
+        cols = []
+        for v in reversed(variables):
+            c = self.cardinality[v]
+            cols.append((flat % c).to(torch.int32))
+            flat = flat // c
+        return torch.stack(cols[::-1], dim=1)
+
     def induced_width(self, elimination_order):
         raise NotImplementedError("induced_width is outside the accelerated path")
 
@@ -265,7 +359,14 @@ class BeliefPropagation(_Inference):
     def calibrate(self):
         """Calibrated (un-normalised) clique and sepset beliefs without evidence, ExactInference.py:897-945.
         One collect + one distribute pass on the GPU reaches the fixed point the reference iterates to."""
-        cp = self._jt_plan([], emit_beliefs=True)
+        self._calibrate(reduce_max=False)
+
+    def _calibrate(self, reduce_max: bool):
+        key = ("jt-beliefs", reduce_max)
+        cp = self._plans.get(key)
+        if cp is None:
+            cp = CompiledPlan(PL.compile_jt_plan(self._jt, [], None, emit_beliefs=True, reduce_max=reduce_max), self.dtype)
+            self._plans[key] = cp
         out = self._run(cp, np.zeros((1, 0), dtype=np.int32)).cpu().numpy()[0]
         self.clique_beliefs = {}
         self.sepset_beliefs = {}
@@ -317,6 +418,31 @@ class BeliefPropagation(_Inference):
         out = self._run(cp, states).cpu().numpy()[0]
         self._warn_nan(out)
         return self._to_factor(variables, out.reshape([self.cardinality[v] for v in variables]))
+
+    def max_calibrate(self):
+        """ExactInference.py:947-995: max-calibrated clique and sepset beliefs (messages reduced with max)."""
+        self._calibrate(reduce_max=True)
+
+    def map_query(self, variables=None, evidence=None, virtual_evidence=None, show_progress=True):
+        """ExactInference.py:1222-1317: argmax assignment of the (un-pruned, BP-mode) joint over `variables`."""
+        evidence = dict(evidence) if evidence is not None else {}
+        if virtual_evidence is not None and isinstance(self.model, DiscreteBayesianNetwork):
+            ve = VariableElimination(self.model, dtype=self.dtype)
+            sub = BeliefPropagation(ve._virtual(virtual_evidence), dtype=self.dtype)
+            virt = {"__" + str(c.variables[0]): 0 for c in virtual_evidence}
+            return sub.map_query(variables, {**evidence, **virt}, None, show_progress)
+        if not variables:
+            seen = []
+            for c in self._jt.cliques:
+                for v in c:
+                    if v not in seen and v not in evidence:
+                        seen.append(v)
+            variables = seen
+        joint = self.query(list(variables), evidence=evidence, joint=True)
+        torch = require_cuda()
+        t = torch.from_numpy(np.ascontiguousarray(joint.values.reshape(1, -1))).cuda()
+        idx = int(VariableElimination._argmax_rows(self, t)[0].item())
+        return VariableElimination._decode(self, list(variables), idx)
 
     def marginals_plan(self, evidence_vars, variables=None) -> CompiledPlan:
         """Compiled all-marginals plan for one evidence-variable signature (bench / batched callers)."""

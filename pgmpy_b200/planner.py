@@ -150,6 +150,7 @@ def compile_factor_ve_plan(
     elimination_order: Optional[Sequence[Hashable]] = None,
     rank: Optional[Dict[Hashable, int]] = None,
     meta: Optional[dict] = None,
+    reduce_max: bool = False,
 ) -> Plan:
     """Sum-product variable elimination over an explicit factor list.
 
@@ -193,11 +194,11 @@ def compile_factor_ve_plan(
             for v in t.vars:
                 if v not in evset and v != var and v not in scope:
                     scope.append(v)
-        out = b.contract(touching, scope, level=level)
+        out = b.contract(touching, scope, level=level, reduce_max=reduce_max)
         level += 1
         work.append(out)
     # every remaining factor has scope within `variables`
-    joint_t = b.contract(work, variables, level=level)
+    joint_t = b.contract(work, variables, level=level, reduce_max=reduce_max)
     if joint:
         b.emit(joint_t, normalize, variables)
     else:
@@ -207,7 +208,8 @@ def compile_factor_ve_plan(
             else:
                 m = b.contract([joint_t], [q], level=level + 1)
                 b.emit(m, normalize, [q])
-    m = {"mode": "ve", "variables": tuple(variables), "evidence_vars": tuple(ev), "joint": joint, "order": tuple(order)}
+    m = {"mode": "ve-max" if reduce_max else "ve", "variables": tuple(variables), "evidence_vars": tuple(ev), "joint": joint,
+         "order": tuple(order)}
     m.update(meta or {})
     return b.finalize(m)
 
@@ -219,7 +221,10 @@ def compile_ve_plan(
     joint: bool = True,
     prune: bool = True,
     elimination_order: Optional[Sequence[Hashable]] = None,
+    reduce_max: bool = False,
 ) -> Plan:
+    """reduce_max=True eliminates with max instead of sum (DiscreteFactor.maximize): the table the reference's
+    max_marginal takes its maximum of (ExactInference.py:459-526)."""
     kept, factors = _pruned_factors(model, variables, evidence_vars, prune)
     ev = [v for v in evidence_vars]  # all evidence variables survive pruning (base.py:192-194)
     rank = {v: i for i, v in enumerate(model.nodes())}
@@ -233,6 +238,7 @@ def compile_ve_plan(
         elimination_order=elimination_order,
         rank=rank,
         meta={"kept": tuple(sorted(kept, key=lambda v: rank[v])), "prune": prune},
+        reduce_max=reduce_max,
     )
 
 
@@ -347,6 +353,7 @@ def compile_jt_plan(
     normalize: bool = True,
     emit_beliefs: bool = False,
     distribute: str = "auto",
+    reduce_max: bool = False,
 ) -> Plan:
     """Two-pass message passing on the rooted junction tree for one evidence-variable signature.
 
@@ -363,7 +370,7 @@ def compile_jt_plan(
     if distribute == "auto" and not emit_beliefs:
         # Shafer-Shenoy keeps the workspace smallest (messages only: fits shared memory for alarm-class models);
         # belief-update wins when high-degree cliques would recompute their product once per neighbour.
-        cands = [compile_jt_plan(jt, evidence_vars, variables, normalize, False, d) for d in ("ss", "belief")]
+        cands = [compile_jt_plan(jt, evidence_vars, variables, normalize, False, d, reduce_max) for d in ("ss", "belief")]
         cost = [p.operand_loads() for p in cands]
         return cands[0] if cost[0] <= 1.2 * cost[1] else cands[1]
     ev = list(evidence_vars)
@@ -391,7 +398,7 @@ def compile_jt_plan(
         if p < 0:
             continue
         ops = [psi[i]] + [up[c] for c in jt.children[i]]
-        up[i] = b.contract(ops, sep(i, p), level=jt.height[i])
+        up[i] = b.contract(ops, sep(i, p), level=jt.height[i], reduce_max=reduce_max)
     base_level = max(jt.height) + 1
     down: Dict[int, Table] = {}
     belief: Dict[int, Table] = {}
@@ -417,9 +424,9 @@ def compile_jt_plan(
             belief[i] = b.contract([psi[i]] + incoming(i), free[i], level=lvl)
         for c in jt.children[i]:
             if i in belief:
-                down[c] = b.contract([belief[i]], sep(i, c), divisors=[up[c]], level=lvl + 1)
+                down[c] = b.contract([belief[i]], sep(i, c), divisors=[up[c]], level=lvl + 1, reduce_max=reduce_max)
             else:
-                down[c] = b.contract([psi[i]] + incoming(i, exclude=c), sep(i, c), level=lvl + 1)
+                down[c] = b.contract([psi[i]] + incoming(i, exclude=c), sep(i, c), level=lvl + 1, reduce_max=reduce_max)
     final_level = base_level + 2 * (max(jt.depth) + 1)
 
     if emit_beliefs:
@@ -431,7 +438,7 @@ def compile_jt_plan(
                 # sepset belief mu_ip = m[i->p] * m[p->i]
                 mu = b.contract([up[i], down[i]], sep(i, p), level=final_level)
                 b.emit(mu, False, sep(i, p))
-        return b.finalize({"mode": "jt-beliefs", "evidence_vars": tuple(ev), "root": jt.root})
+        return b.finalize({"mode": "jt-max-beliefs" if reduce_max else "jt-beliefs", "evidence_vars": tuple(ev), "root": jt.root})
 
     if variables is None:
         seen = set()

@@ -427,3 +427,53 @@ def test_batch_is_tiled_when_the_workspace_would_be_too_large(torch_cuda):
     cp.MAX_WORKSPACE_BYTES = cp.workspace_bytes(64)
     tiled = cp.run(ev)
     assert torch.equal(tiled, whole)
+
+
+def test_max_product_queries_known_answers(torch_cuda):
+    """max_marginal / map_query / max_calibrate against the reference's own tests:
+    pgmpy/tests/test_inference/test_ExactInference.py:235-282 (VE) and :1086-1110 (BP map_query)."""
+    from pgmpy_b200.inference import BeliefPropagation, VariableElimination
+
+    m = six_node_net()
+    ve = VariableElimination(m)
+    np.testing.assert_almost_equal(ve.max_marginal(), 0.1659, decimal=4)
+    np.testing.assert_almost_equal(ve.max_marginal(["G"]), 0.6, decimal=4)
+    np.testing.assert_almost_equal(ve.max_marginal(["G", "R"]), 0.36, decimal=4)
+    np.testing.assert_almost_equal(ve.max_marginal(["G", "R", "A"]), 0.288, decimal=4)
+    with pytest.raises(ValueError):
+        ve.max_marginal(variables=["J"], evidence={"J": 0})
+    assert ve.map_query() == {"A": 1, "R": 1, "J": 1, "Q": 1, "G": 0, "L": 0}
+    assert ve.map_query(["A", "R", "L"], {"J": 0, "Q": 1, "G": 0}) == {"A": 1, "R": 0, "L": 0}
+    with pytest.raises(ValueError):
+        ve.map_query(variables=["J"], evidence={"J": 0})
+    bp = BeliefPropagation(m)
+    assert bp.map_query() == {"A": 1, "R": 1, "J": 1, "Q": 1, "G": 0, "L": 0}
+    assert bp.map_query(["A", "R", "L"], {"J": 0, "Q": 1, "G": 0}) == {"A": 1, "R": 0, "L": 0}
+    # snow network with named states and virtual evidence (:529-560)
+    s = snow_net()
+    from pgmpy_b200 import TabularCPD
+
+    virt = TabularCPD("Traffic", 2, [[0.3], [0.7]], state_names={"Traffic": ["normal", "slow"]})
+    for algo in (VariableElimination, BeliefPropagation):
+        infer = algo(s)
+        assert infer.map_query(["Snow"], virtual_evidence=[virt]) == {"Snow": "no"}
+        assert infer.map_query(["Risk"], virtual_evidence=[virt]) == {"Risk": "yes"}
+        assert infer.map_query(["Late"], virtual_evidence=[virt]) == {"Late": "yes"}
+    # batched MAP == per-row map_query; max-calibrated beliefs == max-marginals of the joint
+    a = px.get_example_model("alarm")
+    va = VariableElimination(a)
+    ev_vars, states = sample_evidence(a, 64, 5, seed=3)
+    q = [v for v in a.nodes() if v not in ev_vars][:3]
+    got = va.map_query_batch(q, ev_vars, states).cpu().numpy()
+    for r in (0, 17, 63):
+        row = {v: a.states[v][int(sx)] for v, sx in zip(ev_vars, states[r])}
+        want = va.map_query(q, row)
+        assert {v: a.states[v][int(i)] for v, i in zip(q, got[r])} == want
+    asia = px.get_example_model("asia")
+    bpa = BeliefPropagation(asia)
+    bpa.max_calibrate()
+    jt = bpa._jt
+    joint = O.factor_product(*[O.Factor(c, p) for c, p in zip(jt.cliques, jt.potentials)])
+    for c, f in bpa.get_clique_beliefs().items():
+        want = O.maximize(joint, [v for v in joint.variables if v not in c])
+        assert rel_err(f.values, O.reorder(want, list(f.variables))) <= 1e-12
