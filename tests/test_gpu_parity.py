@@ -477,3 +477,36 @@ def test_max_product_queries_known_answers(torch_cuda):
     for c, f in bpa.get_clique_beliefs().items():
         want = O.maximize(joint, [v for v in joint.variables if v not in c])
         assert rel_err(f.values, O.reorder(want, list(f.variables))) <= 1e-12
+
+
+def test_predict_and_predict_probability(torch_cuda):
+    """Batch callers: DiscreteBayesianNetwork.predict / predict_probability vs the oracle's
+    per-row loop, pgmpy/models/DiscreteBayesianNetwork.py:731-989."""
+    import pandas as pd
+
+    from pgmpy_b200.evidence import forward_sample
+
+    m = px.get_example_model("asia")
+    net = O.Net(m)
+    nodes, samples = forward_sample(m, 40, np.random.default_rng(0))
+    frame = pd.DataFrame({v: [m.states[v][int(s)] for s in samples[:, i]] for i, v in enumerate(nodes)})
+    data = frame.drop(columns=["lung", "bronc"])
+    probs = m.predict_probability(data)
+    assert list(probs.columns) == ["lung_yes", "lung_no", "bronc_yes", "bronc_no"]
+    pred = m.predict(data)
+    for r in (0, 7, 39):
+        ev = data.iloc[r].to_dict()
+        joint = O.ve_query(net, ["lung", "bronc"], ev)
+        np.testing.assert_allclose(probs.iloc[r][["lung_yes", "lung_no"]].to_numpy(dtype=float), joint.values.sum(axis=1), rtol=1e-12)
+        np.testing.assert_allclose(probs.iloc[r][["bronc_yes", "bronc_no"]].to_numpy(dtype=float), joint.values.sum(axis=0), rtol=1e-12)
+        i, j = np.unravel_index(np.argmax(joint.values), joint.values.shape)
+        assert (pred.iloc[r]["lung"], pred.iloc[r]["bronc"]) == (m.states["lung"][i], m.states["bronc"][j])
+        assert pred.iloc[r]["smoke"] == data.iloc[r]["smoke"]
+    with_nan = data.copy()
+    with_nan.loc[3, "xray"] = np.nan
+    p2 = m.predict(with_nan)
+    assert p2.loc[3, "xray"] in m.states["xray"] and p2.loc[4, "xray"] == data.loc[4, "xray"]
+    with pytest.raises(ValueError):
+        m.predict(frame)
+    with pytest.raises(ValueError):
+        m.predict_probability(data.assign(bogus=1))
