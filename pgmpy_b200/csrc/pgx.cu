@@ -94,7 +94,7 @@ struct TileItem {
 // One launch covers ALL tile-eligible steps of a dependency level (they are independent): the linear CTA index is
 // mapped to its step through `items` (binary search), so the thousands of tiny steps of a large junction tree cost
 // one launch per level instead of one launch each.
-template <typename T, int MAXK>
+template <typename T, int MAXK, bool RTILE>
 __global__ void __launch_bounds__(256) k_contract_tile(const int32_t* __restrict__ pool,
                                                        const TileItem* __restrict__ items, int n_items, int ev_card_off,
                                                        const T* __restrict__ cst, const T* __restrict__ ws_in,
@@ -236,6 +236,61 @@ __global__ void __launch_bounds__(256) k_contract_tile(const int32_t* __restrict
                 }
                 out[(int64_t)o0 * ldb] = p0;
                 if (two) out[(int64_t)o1 * ldb] = p1;
+            }
+            continue;
+        }
+        if (RTILE && MAXK <= 4 && S > 0 && bt_log2 == 5 && !(flags & (FLAG_DIV | FLAG_MAX)) && TO >= 4) {
+            // GEMM-shaped steps: a thread accumulates RT consecutive output entries at once. An operand whose offset
+            // does not change along that run (it does not contain the fastest output variable) is loaded ONCE per
+            // summed index and reused from a register for all RT outputs, instead of being re-fetched from L1/L2.
+            constexpr int RT = 4;
+            for (int og = warp * RT; og < TO; og += n_warps * RT) {
+                const uint32_t o0 = tile0 + og;
+                if (o0 >= out_size) break;
+                int nr = TO - og < RT ? TO - og : RT;
+                if ((uint32_t)nr > out_size - o0) nr = (int)(out_size - o0);
+                const T* p[RT][MAXK];
+                bool shared[MAXK];
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k) {
+                    shared[k] = true;
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        const int rr = r < nr ? r : 0;
+                        const int32_t off = (k < K) ? s_otab[(og + rr) * K + k] : 0;
+                        p[r][k] = base[k] + (int64_t)off * unit[k];
+                        if (p[r][k] != p[0][k]) shared[k] = false;
+                    }
+                }
+                T acc[RT];
+#pragma unroll
+                for (int r = 0; r < RT; ++r) acc[r] = (T)0;
+                const int32_t* st = s_stab;
+#pragma unroll 2
+                for (int q = 0; q < sum_size; ++q, st += K) {
+                    T prod[RT];
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) prod[r] = (T)1;
+#pragma unroll
+                    for (int k = 0; k < MAXK; ++k) {
+                        if (k < K) {
+                            const int64_t so = (int64_t)st[k] * unit[k];
+                            if (shared[k]) {
+                                const T v = p[0][k][so];
+#pragma unroll
+                                for (int r = 0; r < RT; ++r) prod[r] *= v;
+                            } else {
+#pragma unroll
+                                for (int r = 0; r < RT; ++r) prod[r] *= p[r][k][so];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) acc[r] += prod[r];
+                }
+#pragma unroll
+                for (int r = 0; r < RT; ++r)
+                    if (r < nr) out[(int64_t)(o0 + r) * ldb] = acc[r];
             }
             continue;
         }
@@ -417,6 +472,7 @@ struct LaunchGroup {
     int generic_step = -1;  // >= 0: one launch of the generic kernel for this step
     int first_item = 0, n_items = 0, n_blocks = 0, max_k = 0;
     size_t smem = 0;
+    bool rtile = false;  // the group holds GEMM-shaped steps: use the register-tiled instantiation
 };
 
 struct StepSchedule {
@@ -459,6 +515,7 @@ struct pgx_plan {
     std::vector<StepSchedule> schedules;
     cudaStream_t cap_stream = nullptr;
     int last_graph = 0;
+    int reg_tile = 1;     // register-tile GEMM-shaped steps (PGX_OPT_REG_TILE)
     int batch_levels = 1; // share one launch among the tile-eligible steps of a dependency level
     cudaEvent_t* prof_events = nullptr;  // set only inside pgx_profile_steps
     int step_kernel = 0;  // 0 = auto (tile-cooperative where possible), 1 = generic per-thread kernel only
@@ -657,6 +714,14 @@ int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
         case PGX_OPT_USE_GRAPH:
             plan->use_graph = value ? 1 : 0;
             return PGX_OK;
+        case PGX_OPT_REG_TILE:
+            plan->reg_tile = value ? 1 : 0;
+            for (StepSchedule& c : plan->schedules)
+                if (c.d_items) cudaFree(c.d_items);
+            plan->schedules.clear();
+            for (GraphEntry& g : plan->graphs) cudaGraphExecDestroy(g.exec);
+            plan->graphs.clear();
+            return PGX_OK;
         case PGX_OPT_STEP_KERNEL:
             if (value < 0 || value > 1) return fail(PGX_ERR_INVALID, "step kernel must be 0 or 1");
             plan->step_kernel = (int)value;
@@ -818,6 +883,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                 cur.n_items += 1;
                 cur.n_blocks += (int)n_blocks;
                 cur.max_k = std::max(cur.max_k, s.n_ops);
+                if (s.sum_size >= 4 && s.n_ops >= 2 && s.out_size >= 64) cur.rtile = true;
                 cur.smem = std::max(cur.smem, (size_t)(((s.rec_len + 3) & ~3) + TO * s.n_ops + stab_words) * sizeof(int32_t));
             }
             flush(cur);
@@ -861,15 +927,17 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
 #undef PGX_LAUNCH_STEP
                 } else {
                     const TileItem* d_it = sched->d_items + g.first_item;
-#define PGX_LAUNCH_TILE(MK)                                                                                           \
-    k_contract_tile<T, MK><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off, cst, \
-                                                                      ws, ws, ev, pl->n_ev, B, ldb, bt_log2)
-                    if (g.max_k <= 2)
-                        PGX_LAUNCH_TILE(2);
-                    else if (g.max_k <= 4)
-                        PGX_LAUNCH_TILE(4);
-                    else
-                        PGX_LAUNCH_TILE(8);
+#define PGX_LAUNCH_TILE(MK, RT)                                                                                            \
+    k_contract_tile<T, MK, RT><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off, cst, \
+                                                                          ws, ws, ev, pl->n_ev, B, ldb, bt_log2)
+                    const bool rt = g.rtile && pl->reg_tile && bt_log2 == 5;
+                    if (g.max_k <= 2) {
+                        if (rt) PGX_LAUNCH_TILE(2, true); else PGX_LAUNCH_TILE(2, false);
+                    } else if (g.max_k <= 4) {
+                        if (rt) PGX_LAUNCH_TILE(4, true); else PGX_LAUNCH_TILE(4, false);
+                    } else {
+                        PGX_LAUNCH_TILE(8, false);
+                    }
 #undef PGX_LAUNCH_TILE
                 }
                 ++n;

@@ -510,3 +510,21 @@ def test_predict_and_predict_probability(torch_cuda):
         m.predict(frame)
     with pytest.raises(ValueError):
         m.predict_probability(data.assign(bogus=1))
+
+
+def test_register_tiled_steps_match(torch_cuda):
+    """GEMM-shaped steps through the register-tiled instantiation of k_contract_tile == the plain one."""
+    torch = torch_cuda
+    m = px.get_example_model("diabetes")
+    ev_vars, states = sample_evidence(m, 64, 8, seed=3)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars)
+    cp = _engine()(plan)
+    cp.set_mode("stepwise")
+    ev = torch.from_numpy(states).cuda()
+    cp.set_reg_tile(False)
+    plain = cp.run(ev).clone()
+    cp.set_reg_tile(True)
+    tiled = cp.run(ev)
+    assert float(((tiled - plain).abs() / plain.abs().clamp_min(1e-300)).max()) <= 1e-13
+    want = run_plan(plan.pool, plan.const_blob, states[:4])
+    assert rel_err(tiled[:4].cpu().numpy(), want) <= 1e-12
