@@ -65,7 +65,7 @@ extern "C" {
 
 #define PGX_OPT_STEP_KERNEL 5  /* stepwise mode: 0 auto (tile-cooperative kernel where its tables fit) | 1 generic only */
 
-#define PGX_OPT_REG_TILE 6     /* stepwise mode: register-tile GEMM-shaped steps (default 1) */
+#define PGX_OPT_REG_TILE 6     /* stepwise mode: register-tile GEMM-shaped steps (default 0: measured neutral) */
 
 #define PGX_INFO_N_STEPS 1
 #define PGX_INFO_OUT_ELEMS 2

@@ -515,7 +515,7 @@ struct pgx_plan {
     std::vector<StepSchedule> schedules;
     cudaStream_t cap_stream = nullptr;
     int last_graph = 0;
-    int reg_tile = 1;     // register-tile GEMM-shaped steps (PGX_OPT_REG_TILE)
+    int reg_tile = 0;     // register-tile GEMM-shaped steps (PGX_OPT_REG_TILE); measured neutral-to-slower, off by default
     int batch_levels = 1; // share one launch among the tile-eligible steps of a dependency level
     cudaEvent_t* prof_events = nullptr;  // set only inside pgx_profile_steps
     int step_kernel = 0;  // 0 = auto (tile-cooperative where possible), 1 = generic per-thread kernel only

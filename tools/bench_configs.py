@@ -113,6 +113,9 @@ if __name__ == "__main__":
     if "large" in what:
         bp_all_marginals("pathfinder", 16384)
         bp_all_marginals("diabetes", 2048)
+    if what and what[0] == "one":
+        bp_all_marginals(what[1], int(what[2]), reps=int(what[3]) if len(what) > 3 else 3, reg_tile=False)
+        sys.exit(0)
     if "rtile" in what:
         for name, b in (("pathfinder", 4096), ("diabetes", 1024), ("munin", 64)):
             for rt in (False, True):
