@@ -311,30 +311,8 @@ __global__ void __launch_bounds__(256) k_contract_tile(const int32_t* __restrict
             } else {
                 acc = use_max ? neg_inf<T>() : (T)0;
                 const int32_t* st = s_stab;
-                int q = 0;
-                // these steps are latency bound (ncu: long_scoreboard ~60 % of stalls at 24 warps/SM): issue the
-                // loads of QU summed indices before consuming any of them; the accumulation order is unchanged
-                constexpr int QU = MAXK <= 4 ? 4 : 2;
-                for (; q + QU <= sum_size; q += QU, st += QU * K) {
-                    T v[QU][MAXK];
-#pragma unroll
-                    for (int u = 0; u < QU; ++u)
-#pragma unroll
-                        for (int k = 0; k < MAXK; ++k)
-                            if (k < n_mul) v[u][k] = ptr[k][(int64_t)st[u * K + k] * unit[k]];
-#pragma unroll
-                    for (int u = 0; u < QU; ++u) {
-                        T prod = (T)1;
-#pragma unroll
-                        for (int k = 0; k < MAXK; ++k)
-                            if (k < n_mul) prod *= v[u][k];
-                        if (use_max)
-                            acc = prod > acc ? prod : acc;
-                        else
-                            acc += prod;
-                    }
-                }
-                for (; q < sum_size; ++q, st += K) {
+#pragma unroll 4
+                for (int q = 0; q < sum_size; ++q, st += K) {
                     T prod = (T)1;
 #pragma unroll
                     for (int k = 0; k < MAXK; ++k)
