@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--mode", default="auto", choices=["auto", "fused", "stepwise"])
     ap.add_argument("--fused-warps", type=int, default=0)
     ap.add_argument("--fused-kernel", default="auto", choices=["auto", "generic", "tables-smem", "tables-global"])
-    ap.add_argument("--step-kernel", default="auto", choices=["auto", "generic"])
+    ap.add_argument("--step-kernel", default="auto", choices=["auto", "generic", "tile64"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

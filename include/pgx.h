@@ -63,7 +63,8 @@ extern "C" {
 #define PGX_OPT_FUSED_KERNEL 4 /* 0 auto | 1 generic addressing | 2 offset tables + shared-memory work tables |
                                   3 offset tables + global work tables */
 
-#define PGX_OPT_STEP_KERNEL 5  /* stepwise mode: 0 auto (tile-cooperative kernel where its tables fit) | 1 generic only */
+#define PGX_OPT_STEP_KERNEL 5  /* stepwise mode: 0 auto (tile-cooperative kernel, 32-bit addressing) | 1 generic only |
+                                  2 tile-cooperative kernel with 64-bit addressing */
 
 #define PGX_OPT_REG_TILE 6     /* stepwise mode: register-tile GEMM-shaped steps (default 0: measured neutral) */
 

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpgx.so")
+LIB_PATH = os.environ.get("PGX_LIB", os.path.join(HERE, "libpgx.so"))  # PGX_LIB: tuning builds only
 
 PGX_F64, PGX_F32 = 0, 1
 MODE_AUTO, MODE_STEPWISE, MODE_FUSED = 0, 1, 2

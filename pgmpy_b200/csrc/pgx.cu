@@ -43,6 +43,13 @@ int fail(int code, const std::string& msg) {
 
 using namespace pgx;
 
+#ifndef PGX_TILE32_MINB
+#define PGX_TILE32_MINB 6  // same knob for the 32-bit-addressed tile kernel
+#endif
+#ifndef PGX_TILE_MINB
+#define PGX_TILE_MINB 5  // CTAs per SM the tile kernel is compiled for (register cap 65536 / (256 * N)); measured 1..6
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
@@ -95,7 +102,7 @@ struct TileItem {
 // mapped to its step through `items` (binary search), so the thousands of tiny steps of a large junction tree cost
 // one launch per level instead of one launch each.
 template <typename T, int MAXK, bool RTILE>
-__global__ void __launch_bounds__(256) k_contract_tile(const int32_t* __restrict__ pool,
+__global__ void __launch_bounds__(256, (RTILE || MAXK > 4) ? 1 : PGX_TILE_MINB) k_contract_tile(const int32_t* __restrict__ pool,
                                                        const TileItem* __restrict__ items, int n_items, int ev_card_off,
                                                        const T* __restrict__ cst, const T* __restrict__ ws_in,
                                                        T* __restrict__ ws_out, const int32_t* __restrict__ ev, int n_ev,
@@ -332,6 +339,190 @@ __global__ void __launch_bounds__(256) k_contract_tile(const int32_t* __restrict
                 acc = (r != r) ? (T)0 : r;
             }
             out[(int64_t)o * ldb] = acc;
+        }
+    }
+}
+
+// K2, tile-cooperative form with 32-bit addressing (the default). Same two phases as k_contract_tile, but every
+// operand lives in ONE address space: pgx_run_batch copies the batch-invariant tables to the head of the workspace,
+// so an operand element is `wsb[u32 index]` whatever its kind. Per operand the thread keeps two 32-bit values (row
+// base, elements per entry) instead of two 64-bit ones, which brings the kernel to <= 40 registers — the step kernels
+// are latency bound (profiles/r01_diabetes_tile_kernel_ncu.md), so resident warps are what buys throughput.
+template <typename T, int MAXK>
+__global__ void __launch_bounds__(256, MAXK <= 4 ? PGX_TILE32_MINB : 3) k_contract_tile32(const int32_t* __restrict__ pool,
+                                                                            const TileItem* __restrict__ items, int n_items,
+                                                                            int ev_card_off, const T* __restrict__ ws_in,
+                                                                            T* __restrict__ ws_out, uint32_t ws_off0,
+                                                                            const int32_t* __restrict__ ev, int n_ev,
+                                                                            int64_t B, uint32_t ldb, int bt_log2) {
+    extern __shared__ int32_t s_mem[];
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (items[mid].blk_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const TileItem it = items[lo];
+    const int local = (int)blockIdx.x - it.blk_begin;
+    const int tile_x = local / it.b_blocks;
+    const int b_block = local - tile_x * it.b_blocks;
+    const int TO = it.TO, btb = it.btb, rec_len = it.rec_len;
+
+    int32_t* s_rec = s_mem;
+    for (int i = threadIdx.x; i < rec_len; i += blockDim.x) s_rec[i] = pool[it.rec_off + i];
+    __syncthreads();
+    const int A = s_rec[0], S = s_rec[1], K = s_rec[2], flags = s_rec[3];
+    const int opw = OP_FIXED + A + S;
+    const int32_t* odims = s_rec + STEP_FIXED;
+    const int32_t* sdims = odims + A;
+    const int32_t* ops = sdims + S;
+    const uint32_t out_size = (uint32_t)s_rec[4];
+    const int sum_size = s_rec[6];
+    int32_t* s_otab = s_mem + ((rec_len + 3) & ~3);
+    int32_t* s_stab = s_otab + TO * K;
+    const uint32_t tile0 = (uint32_t)tile_x * (uint32_t)TO;
+    for (int t = threadIdx.x; t < TO; t += blockDim.x) {
+        uint32_t rem = tile0 + t;
+        int32_t off[MAXK];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) off[k] = 0;
+        if (rem < out_size) {
+            for (int a = A - 1; a >= 0; --a) {
+                const uint32_t d = (uint32_t)odims[a];
+                const uint32_t q = rem / d;
+                const int32_t digit = (int32_t)(rem - q * d);
+                rem = q;
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k)
+                    if (k < K) off[k] += digit * ops[k * opw + OP_FIXED + a];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+            if (k < K) s_otab[t * K + k] = off[k];
+    }
+    for (int qi = threadIdx.x; qi < sum_size; qi += blockDim.x) {
+        uint32_t rem = (uint32_t)qi;
+        int32_t off[MAXK];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) off[k] = 0;
+        for (int a = S - 1; a >= 0; --a) {
+            const uint32_t d = (uint32_t)sdims[a];
+            const uint32_t q = rem / d;
+            const int32_t digit = (int32_t)(rem - q * d);
+            rem = q;
+#pragma unroll
+            for (int k = 0; k < MAXK; ++k)
+                if (k < K) off[k] += digit * ops[k * opw + OP_FIXED + A + a];
+        }
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+            if (k < K) s_stab[qi * K + k] = off[k];
+    }
+    __syncthreads();
+
+    int n_mul = K;
+    if (flags & FLAG_DIV)
+        while (n_mul > 0 && (ops[(n_mul - 1) * opw] & 0x100)) --n_mul;
+    const bool use_max = (flags & FLAG_MAX) != 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int bt = 1 << bt_log2;
+    const int o_per_warp = 32 >> bt_log2;
+    const int o_sub = lane >> bt_log2;
+    const uint32_t out_base = ws_off0 + (uint32_t)s_rec[8] * ldb;  // out work offset fits 32 bits here (host checked)
+    const int32_t* ev_card = pool + ev_card_off;
+    const int og_step = n_warps * o_per_warp;
+    for (int tb = 0; tb < btb; ++tb) {
+        const int64_t b = ((int64_t)b_block * btb + tb) * bt + (lane & (bt - 1));
+        if (b >= B) continue;  // no barriers below
+        uint32_t rowb[MAXK], unit[MAXK];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) {
+            rowb[k] = 0;
+            unit[k] = 0;
+            if (k < K) {
+                const int32_t* op = ops + k * opw;
+                uint32_t e = (uint32_t)op[1];
+                const int ne = op[3];
+                if (ne > 0) {
+                    const int32_t* pairs = s_rec + op[4];
+                    for (int j = 0; j < ne; ++j) {
+                        const int slot = pairs[2 * j];
+                        int32_t st = ev[b * n_ev + slot];
+                        const int32_t card = ev_card[slot];
+                        st = st < 0 ? 0 : (st >= card ? card - 1 : st);
+                        e += (uint32_t)(st * pairs[2 * j + 1]);
+                    }
+                }
+                if ((op[0] & 0xFF) == 1) {
+                    unit[k] = ldb;
+                    rowb[k] = ws_off0 + e * ldb + (uint32_t)b;
+                } else {
+                    unit[k] = 1;
+                    rowb[k] = e;
+                }
+            }
+        }
+        const uint32_t outb = out_base + (uint32_t)b;
+        if (S == 0 && !(flags & FLAG_DIV)) {
+            for (int og = warp * o_per_warp + o_sub; og < TO; og += 2 * og_step) {
+                const uint32_t o0 = tile0 + og, o1 = o0 + og_step;
+                if (o0 >= out_size) break;
+                const bool two = (og + og_step < TO) && (o1 < out_size);
+                const int32_t* ot0 = s_otab + og * K;
+                const int32_t* ot1 = ot0 + (two ? og_step * K : 0);
+                T p0 = (T)1, p1 = (T)1;
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k) {
+                    if (k < K) {
+                        const T v0 = ws_in[rowb[k] + (uint32_t)ot0[k] * unit[k]];
+                        const T v1 = ws_in[rowb[k] + (uint32_t)ot1[k] * unit[k]];
+                        p0 *= v0;
+                        p1 *= v1;
+                    }
+                }
+                ws_out[outb + o0 * ldb] = p0;
+                if (two) ws_out[outb + o1 * ldb] = p1;
+            }
+            continue;
+        }
+        for (int og = warp * o_per_warp + o_sub; og < TO; og += og_step) {
+            const uint32_t o = tile0 + og;
+            if (o >= out_size) break;
+            const int32_t* ot = s_otab + og * K;
+            uint32_t p[MAXK];
+#pragma unroll
+            for (int k = 0; k < MAXK; ++k) p[k] = (k < K) ? rowb[k] + (uint32_t)ot[k] * unit[k] : 0;
+            T acc;
+            if (S == 0) {
+                T prod = (T)1;
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k)
+                    if (k < n_mul) prod *= ws_in[p[k]];
+                acc = prod;
+            } else {
+                acc = use_max ? neg_inf<T>() : (T)0;
+                const int32_t* st = s_stab;
+#pragma unroll 4
+                for (int q = 0; q < sum_size; ++q, st += K) {
+                    T prod = (T)1;
+#pragma unroll
+                    for (int k = 0; k < MAXK; ++k)
+                        if (k < n_mul) prod *= ws_in[p[k] + (uint32_t)st[k] * unit[k]];
+                    if (use_max)
+                        acc = prod > acc ? prod : acc;
+                    else
+                        acc += prod;
+                }
+            }
+            if (flags & FLAG_DIV) {
+                T den = (T)1;
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k)
+                    if (k >= n_mul && k < K) den *= ws_in[p[k]];
+                const T r = acc / den;
+                acc = (r != r) ? (T)0 : r;
+            }
+            ws_out[outb + o * ldb] = acc;
         }
     }
 }
@@ -697,7 +888,9 @@ void pgx_plan_destroy(pgx_plan* plan) {
 size_t pgx_workspace_bytes(const pgx_plan* plan, int64_t B) {
     if (!plan || B <= 0) return 0;
     const size_t item = plan->dtype == PGX_F64 ? 8 : 4;
-    return (size_t)plan->ws_entries * (size_t)pgx_batch_ld(B) * item;
+    // head: room for a copy of the batch-invariant tables (32-bit-addressed step kernel); then the work tables
+    const size_t head = ((size_t)plan->table_entries + 31) / 32 * 32;
+    return (head + (size_t)plan->ws_entries * (size_t)pgx_batch_ld(B)) * item;
 }
 
 int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
@@ -723,7 +916,7 @@ int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
             plan->graphs.clear();
             return PGX_OK;
         case PGX_OPT_STEP_KERNEL:
-            if (value < 0 || value > 1) return fail(PGX_ERR_INVALID, "step kernel must be 0 or 1");
+            if (value < 0 || value > 2) return fail(PGX_ERR_INVALID, "step kernel must be 0, 1 or 2");
             plan->step_kernel = (int)value;
             return PGX_OK;
         case PGX_OPT_FUSED_KERNEL:
@@ -760,7 +953,9 @@ template <typename T>
 int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t B, cudaStream_t st) {
     const int64_t ldb = pgx_batch_ld(B);
     const T* cst = (const T*)pl->blob;
-    T* ws = (T*)ws_v;
+    T* ws_all = (T*)ws_v;
+    const size_t ws_off0 = ((size_t)pl->table_entries + 31) / 32 * 32;
+    T* ws = ws_all + ws_off0;  // work tables start after the head reserved for the table copy
     T* out = (T*)out_v;
     int mode = pl->mode;
     if (mode == PGX_MODE_AUTO) mode = (pl->max_joint <= 8192 && B >= 2048) ? PGX_MODE_FUSED : PGX_MODE_STEPWISE;
@@ -853,7 +1048,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
             for (size_t si = 0; si < pl->steps.size(); ++si) {
                 const StepInfo& s = pl->steps[si];
                 const int64_t stab_words = s.sum_size * s.n_ops;
-                const bool tile_ok = s.n_ops <= 8 && stab_words <= 8192 && pl->step_kernel != 1;
+                const bool tile_ok = s.n_ops <= 8 && stab_words <= 8192 && pl->step_kernel != 1;  // 0 tile32, 2 tile64
                 if (!tile_ok || s.level != cur_level || !pl->batch_levels) flush(cur);
                 cur_level = s.level;
                 if (!tile_ok) {
@@ -900,10 +1095,14 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
             pl->schedules.push_back(ns);
             sched = &pl->schedules.back();
         }
+        // 32-bit addressing needs every element index (table copy + work tables) below 2^32
+        const bool idx32 = pl->step_kernel == 0 && ws_off0 + (size_t)pl->ws_entries * (size_t)ldb < (1ULL << 32) &&
+                           pl->ws_entries < (1LL << 31);
         auto enqueue = [&](cudaStream_t qs) -> int {
             int n = 0;
             cudaEvent_t* evs = pl->prof_events;
             int ev_idx = 0;
+            if (idx32) cudaMemcpyAsync(ws_all, cst, (size_t)pl->table_entries * sizeof(T), cudaMemcpyDeviceToDevice, qs);
             for (const LaunchGroup& g : sched->groups) {
                 if (g.generic_step >= 0) {
                     const StepInfo& s = pl->steps[g.generic_step];
@@ -931,7 +1130,19 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
     k_contract_tile<T, MK, RT><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off, cst, \
                                                                           ws, ws, ev, pl->n_ev, B, ldb, bt_log2)
                     const bool rt = g.rtile && pl->reg_tile && bt_log2 == 5;
-                    if (g.max_k <= 2) {
+                    if (idx32 && !rt) {
+#define PGX_LAUNCH_TILE32(MK)                                                                                          \
+    k_contract_tile32<T, MK><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off, ws_all, \
+                                                                        ws_all, (uint32_t)ws_off0, ev, pl->n_ev, B,        \
+                                                                        (uint32_t)ldb, bt_log2)
+                        if (g.max_k <= 2)
+                            PGX_LAUNCH_TILE32(2);
+                        else if (g.max_k <= 4)
+                            PGX_LAUNCH_TILE32(4);
+                        else
+                            PGX_LAUNCH_TILE32(8);
+#undef PGX_LAUNCH_TILE32
+                    } else if (g.max_k <= 2) {
                         if (rt) PGX_LAUNCH_TILE(2, true); else PGX_LAUNCH_TILE(2, false);
                     } else if (g.max_k <= 4) {
                         if (rt) PGX_LAUNCH_TILE(4, true); else PGX_LAUNCH_TILE(4, false);

@@ -68,8 +68,8 @@ class CompiledPlan:
     # ---- options / info ----------------------------------------------------------------------
     def set_mode(self, mode: str = "auto", fused_warps: int = 0, fused_kernel: str = "auto", step_kernel: str = "auto"):
         """mode: auto | stepwise | fused.  fused_kernel: auto | generic | tables-smem | tables-global.
-        step_kernel: auto (tile-cooperative where possible) | generic."""
-        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_STEP_KERNEL, {"auto": 0, "generic": 1}[step_kernel]))
+        step_kernel: auto (tile-cooperative, 32-bit addressing) | generic | tile64."""
+        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_STEP_KERNEL, {"auto": 0, "generic": 1, "tile64": 2}[step_kernel]))
         m = {"auto": N.MODE_AUTO, "stepwise": N.MODE_STEPWISE, "fused": N.MODE_FUSED}[mode]
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_MODE, m))
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_FUSED_WARPS, fused_warps))

@@ -33,7 +33,8 @@ def _engine():
 
 
 # (mode, fused kernel, step kernel)
-EXEC_VARIANTS = [("stepwise", "auto", "auto"), ("stepwise", "auto", "generic"), ("fused", "generic", "auto"),
+EXEC_VARIANTS = [("stepwise", "auto", "auto"), ("stepwise", "auto", "generic"), ("stepwise", "auto", "tile64"),
+                 ("fused", "generic", "auto"),
                  ("fused", "tables-smem", "auto"), ("fused", "tables-global", "auto")]
 
 
@@ -119,7 +120,7 @@ def test_large_models_stepwise_vs_oracle(torch_cuda, name):
     ev_vars, states = sample_evidence(m, 3, 8, seed=2)
     plan = compile_jt_plan(jt, ev_vars)
     want = run_plan(plan.pool, plan.const_blob, states)
-    for step_kernel in ("auto", "generic"):
+    for step_kernel in ("auto", "generic", "tile64"):
         cp = _engine()(plan)
         cp.set_mode("stepwise", 0, "auto", step_kernel)
         got = cp.run_host(states)
