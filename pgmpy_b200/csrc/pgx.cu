@@ -44,7 +44,7 @@ int fail(int code, const std::string& msg) {
 using namespace pgx;
 
 #ifndef PGX_TILE32_MINB
-#define PGX_TILE32_MINB 6  // same knob for the 32-bit-addressed tile kernel
+#define PGX_TILE32_MINB 8  // same knob for the 32-bit-addressed tile kernel: 32 registers, 64 warps/SM (measured 4..8: 8 is best even with 40 B of spills)
 #endif
 #ifndef PGX_TILE_MINB
 #define PGX_TILE_MINB 5  // CTAs per SM the tile kernel is compiled for (register cap 65536 / (256 * N)); measured 1..6
