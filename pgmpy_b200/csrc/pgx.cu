@@ -958,7 +958,13 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
     T* ws = ws_all + ws_off0;  // work tables start after the head reserved for the table copy
     T* out = (T*)out_v;
     int mode = pl->mode;
-    if (mode == PGX_MODE_AUTO) mode = (pl->max_joint <= 8192 && B >= 2048) ? PGX_MODE_FUSED : PGX_MODE_STEPWISE;
+    if (mode == PGX_MODE_AUTO) {
+        // whole-plan kernel for small models when its work tables fit shared memory, or when every step takes the
+        // 64-register fast path; otherwise (hepar2-class belief-update plans, large tables) the step sequence wins
+        const bool fits_smem = (size_t)pl->ws_entries * 32 * sizeof(T) + (size_t)pl->n_ev * 128 <= 226 * 1024;
+        mode = (pl->micro.ok && pl->max_joint <= 8192 && B >= 2048 && (fits_smem || pl->micro.all_fast)) ? PGX_MODE_FUSED
+                                                                                                         : PGX_MODE_STEPWISE;
+    }
     int64_t launches = 0;
     if (mode == PGX_MODE_FUSED && pl->micro.ok && pl->fused_kernel != 1) {
         // table-driven kernel; work tables in shared memory when a row of 32 evidence sets fits

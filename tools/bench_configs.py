@@ -83,7 +83,7 @@ def mixed_ve(name, batch=262144, n_sig=16):
                       "alg_GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / PEAK}), flush=True)
 
 
-def bp_all_marginals(name, batch, k=8, reps=3, reg_tile=True):
+def bp_all_marginals(name, batch, k=8, reps=3, reg_tile=False):
     """configs[3]/[4]: large-table junction-tree all-marginals (pathfinder, diabetes, munin)."""
     m = px.get_example_model(name)
     bp = BeliefPropagation(m)
