@@ -200,6 +200,27 @@ class VariableElimination(_Inference):
         cp = self._plan(list(variables), list(evidence_vars), joint, elimination_order)
         return self._run(cp, evidence_states)
 
+    def marginals_plan(self, evidence_vars, variables=None) -> CompiledPlan:
+        """One plan holding the VE-mode posterior of every unobserved variable (or of `variables`), each with its own
+        pruned network exactly as `query([v], evidence)` would use — the reference's way of asking for all-variable
+        marginals, as a single launch."""
+        order = list(self.model.nodes())
+        evset = set(evidence_vars)
+        variables = [v for v in order if v not in evset] if variables is None else list(variables)
+        self._check_query(variables, {v: None for v in evidence_vars})
+        key = ("ve-multi", tuple(variables), tuple(evidence_vars))
+        cp = self._plans.get(key)
+        if cp is None:
+            plan = PL.compile_ve_multi_plan(self.model, [[v] for v in variables], list(evidence_vars))
+            cp = CompiledPlan(plan, self.dtype)
+            self._plans[key] = cp
+        return cp
+
+    def marginals_batch(self, evidence_vars, evidence_states, variables=None):
+        """CUDA tensor [B, sum card]: per-variable VE-mode posteriors for B evidence sets (segments in
+        `marginals_plan(...).plan.segments`)."""
+        return self._run(self.marginals_plan(evidence_vars, variables), evidence_states)
+
     def query_batch_mixed(self, variables, evidence_rows, joint=True):
         """Mixed-evidence batch: `evidence_rows` is a list of {var: state name} dicts whose observed SETS may
         differ from row to row (what DiscreteBayesianNetwork.predict_probability feeds the reference one row at a

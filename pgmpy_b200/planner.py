@@ -151,6 +151,7 @@ def compile_factor_ve_plan(
     rank: Optional[Dict[Hashable, int]] = None,
     meta: Optional[dict] = None,
     reduce_max: bool = False,
+    builder: Optional[PlanBuilder] = None,
 ) -> Plan:
     """Sum-product variable elimination over an explicit factor list.
 
@@ -161,12 +162,12 @@ def compile_factor_ve_plan(
     variables = list(variables)
     ev = list(evidence_vars)
     evset = set(ev)
-    b = PlanBuilder(card, ev)
+    b = builder if builder is not None else PlanBuilder(card, ev)
     work: List[Table] = []
     for scope, vals, key in factors:
         if all(v in evset for v in scope):
             continue
-        work.append(b.add_const(scope, vals, key=None))
+        work.append(b.add_const(scope, vals, key=key if builder is not None else None))
     free_scopes = [[v for v in t.vars if v not in evset] for t in work]
     present = set(v for sc in free_scopes for v in sc)
     for q in variables:
@@ -211,6 +212,8 @@ def compile_factor_ve_plan(
     m = {"mode": "ve-max" if reduce_max else "ve", "variables": tuple(variables), "evidence_vars": tuple(ev), "joint": joint,
          "order": tuple(order)}
     m.update(meta or {})
+    if builder is not None:
+        return m  # the caller finalizes the shared builder
     return b.finalize(m)
 
 
@@ -240,6 +243,26 @@ def compile_ve_plan(
         meta={"kept": tuple(sorted(kept, key=lambda v: rank[v])), "prune": prune},
         reduce_max=reduce_max,
     )
+
+
+def compile_ve_multi_plan(
+    model: DiscreteBayesianNetwork, queries: Sequence[Sequence[Hashable]], evidence_vars: Sequence[Hashable] = ()
+) -> Plan:
+    """Several VE-mode queries that share one evidence-variable set, as ONE plan (one launch): every query keeps its
+    own pruned factor set (pruning depends on the query variables), identical (renormalised) CPTs
+    are stored once, the per-query elimination chains are independent and run level-parallel; one normalised output
+    segment per query. This is how "all-variable marginals" is asked of the reference (one query([v], e) per
+    variable) without paying one launch per variable."""
+    ev = list(evidence_vars)
+    card = model.get_cardinality()
+    rank = {v: i for i, v in enumerate(model.nodes())}
+    b = PlanBuilder(card, ev)
+    metas = []
+    for variables in queries:
+        _, factors = _pruned_factors(model, list(variables), ev, True)
+        metas.append(compile_factor_ve_plan(factors, card, list(variables), ev, joint=True, normalize=True, rank=rank, builder=b))
+    return b.finalize({"mode": "ve-multi", "evidence_vars": tuple(ev), "queries": tuple(tuple(q) for q in queries),
+                       "orders": tuple(m["order"] for m in metas)})
 
 
 # ---------------------------------------------------------------------------------------------

@@ -573,3 +573,17 @@ def test_fp32_mode_larger_models(torch_cuda, name):
     got = cp.run_host(states)
     assert np.isfinite(got).all()
     assert np.max(np.abs(got - want)) <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["alarm", "hepar2"])
+def test_ve_marginals_batch_single_plan_vs_reference_golden(torch_cuda, name):
+    """VariableElimination.marginals_batch: every per-variable VE-mode posterior (own pruning each) from one plan."""
+    from pgmpy_b200.inference import VariableElimination
+
+    g = load_golden(name)
+    m = px.get_example_model(name)
+    ve = VariableElimination(m)
+    cp = ve.marginals_plan(g["ev_vars"])
+    out = ve.marginals_batch(g["ev_vars"], g["ev_states"]).cpu().numpy()
+    col = {s.vars[0]: (s.out_offset, s.table.size) for s in cp.plan.segments}
+    assert max(rel_err(out[case, col[q][0] : col[q][0] + col[q][1]], want) for case, q, want in g["ve"]) <= 1e-12

@@ -198,3 +198,17 @@ def test_microprogram_tables_match_plan_interpreter(name):
     plan = compile_ve_plan(m, free[:3], ev_vars, joint=False)
     got, _ = hostsim_micro_run(plan, states)
     assert rel_err(got, run_plan(plan.pool, plan.const_blob, states)) <= 1e-13
+
+
+@pytest.mark.parametrize("name", ["asia", "alarm", "win95pts"])
+def test_multi_query_ve_plan_matches_reference_golden(name):
+    """All VE-mode single-variable posteriors of one evidence signature in ONE plan (each query keeps its own pruning)."""
+    from pgmpy_b200.planner import compile_ve_multi_plan
+
+    g = load_golden(name)
+    m = px.get_example_model(name)
+    free = [v for v in m.nodes() if v not in g["ev_vars"]]
+    plan = compile_ve_multi_plan(m, [[v] for v in free], g["ev_vars"])
+    out = run_plan(plan.pool, plan.const_blob, g["ev_states"])
+    col = {s.vars[0]: (s.out_offset, s.table.size) for s in plan.segments}
+    assert max(rel_err(out[case, col[q][0] : col[q][0] + col[q][1]], want) for case, q, want in g["ve"]) <= 1e-12

@@ -46,6 +46,20 @@ def alarm_ve(batch=1024):
         for cp, o in zip(plans, outs):
             cp.run(ev, out=o)
 
+    t0 = time.perf_counter()
+    multi = ve.marginals_plan(ev_vars)
+    multi_compile_s = time.perf_counter() - t0
+    mout = torch.empty((batch, multi.out_elems), dtype=torch.float64, device="cuda")
+    ms_multi = timed(lambda: multi.run(ev, out=mout))
+    for cp, o, seg in zip(plans, outs, multi.plan.segments):
+        cp.run(ev, out=o)
+        assert torch.allclose(o, mout[:, seg.out_offset : seg.out_offset + seg.table.size], rtol=1e-13, atol=0)
+    print(json.dumps({"config": "alarm VE all-variable marginals, ONE plan holding all 32 pruned queries", "batch": batch,
+                      "steps": multi.plan.n_steps, "plan_compile_s": round(multi_compile_s, 2), "mode": multi.last_mode,
+                      "variant": multi.last_variant, "ms_per_batch": ms_multi, "evidence_queries_per_sec": batch / ms_multi * 1e3,
+                      "single_variable_queries_per_sec": batch * len(plans) / ms_multi * 1e3,
+                      "alg_GBps": multi.plan.algorithmic_bytes(batch) / ms_multi / 1e6,
+                      "frac_of_hbm_peak": multi.plan.algorithmic_bytes(batch) / ms_multi / 1e6 / PEAK}), flush=True)
     ms = timed(run)
     alg = sum(cp.plan.algorithmic_bytes(batch) for cp in plans)
     print(json.dumps({"config": "alarm VE all-variable marginals (one pruned plan per query variable)", "batch": batch,
