@@ -43,6 +43,9 @@ int fail(int code, const std::string& msg) {
 
 using namespace pgx;
 
+#ifndef PGX_TILE32_RT_MINB
+#define PGX_TILE32_RT_MINB 4  // CTAs per SM for the register-tiled instantiation of the 32-bit tile kernel
+#endif
 #ifndef PGX_TILE32_MINB
 #define PGX_TILE32_MINB 8  // same knob for the 32-bit-addressed tile kernel: 32 registers, 64 warps/SM (measured 4..8: 8 is best even with 40 B of spills)
 #endif
@@ -348,8 +351,8 @@ __global__ void __launch_bounds__(256, (RTILE || MAXK > 4) ? 1 : PGX_TILE_MINB) 
 // so an operand element is `wsb[u32 index]` whatever its kind. Per operand the thread keeps two 32-bit values (row
 // base, elements per entry) instead of two 64-bit ones, which brings the kernel to <= 40 registers — the step kernels
 // are latency bound (profiles/r01_diabetes_tile_kernel_ncu.md), so resident warps are what buys throughput.
-template <typename T, int MAXK>
-__global__ void __launch_bounds__(256, MAXK <= 4 ? PGX_TILE32_MINB : 3) k_contract_tile32(const int32_t* __restrict__ pool,
+template <typename T, int MAXK, bool RTILE>
+__global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ? PGX_TILE32_MINB : 3)) k_contract_tile32(const int32_t* __restrict__ pool,
                                                                             const TileItem* __restrict__ items, int n_items,
                                                                             int ev_card_off, const T* __restrict__ ws_in,
                                                                             T* __restrict__ ws_out, uint32_t ws_off0,
@@ -482,6 +485,60 @@ __global__ void __launch_bounds__(256, MAXK <= 4 ? PGX_TILE32_MINB : 3) k_contra
                 }
                 ws_out[outb + o0 * ldb] = p0;
                 if (two) ws_out[outb + o1 * ldb] = p1;
+            }
+            continue;
+        }
+        if (RTILE && MAXK <= 4 && S > 0 && bt_log2 == 5 && !(flags & (FLAG_DIV | FLAG_MAX)) && TO >= 4) {
+            // RT consecutive output entries per thread: an operand that does not contain the fastest output variable
+            // has the same row for all of them and is loaded once per summed index (fewer L2->L1 bytes on GEMM-shaped
+            // steps whose small operands are re-read by every output entry)
+            constexpr int RT = 4;
+            for (int og = warp * RT; og < TO; og += n_warps * RT) {
+                const uint32_t o0 = tile0 + og;
+                if (o0 >= out_size) break;
+                int nr = TO - og < RT ? TO - og : RT;
+                if ((uint32_t)nr > out_size - o0) nr = (int)(out_size - o0);
+                uint32_t p[RT][MAXK];
+                bool same[MAXK];
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k) {
+                    same[k] = true;
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        const int rr = r < nr ? r : 0;
+                        p[r][k] = (k < K) ? rowb[k] + (uint32_t)s_otab[(og + rr) * K + k] * unit[k] : 0;
+                        if (p[r][k] != p[0][k]) same[k] = false;
+                    }
+                }
+                T acc[RT];
+#pragma unroll
+                for (int r = 0; r < RT; ++r) acc[r] = (T)0;
+                const int32_t* st = s_stab;
+#pragma unroll 2
+                for (int q = 0; q < sum_size; ++q, st += K) {
+                    T prod[RT];
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) prod[r] = (T)1;
+#pragma unroll
+                    for (int k = 0; k < MAXK; ++k) {
+                        if (k < K) {
+                            const uint32_t so = (uint32_t)st[k] * unit[k];
+                            if (same[k]) {
+                                const T v = ws_in[p[0][k] + so];
+#pragma unroll
+                                for (int r = 0; r < RT; ++r) prod[r] *= v;
+                            } else {
+#pragma unroll
+                                for (int r = 0; r < RT; ++r) prod[r] *= ws_in[p[r][k] + so];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) acc[r] += prod[r];
+                }
+#pragma unroll
+                for (int r = 0; r < RT; ++r)
+                    if (r < nr) ws_out[outb + (o0 + r) * ldb] = acc[r];
             }
             continue;
         }
@@ -1137,17 +1194,18 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
     k_contract_tile<T, MK, RT><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off, cst, \
                                                                           ws, ws, ev, pl->n_ev, B, ldb, bt_log2)
                     const bool rt = g.rtile && pl->reg_tile && bt_log2 == 5;
-                    if (idx32 && !rt) {
-#define PGX_LAUNCH_TILE32(MK)                                                                                          \
-    k_contract_tile32<T, MK><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off, ws_all, \
-                                                                        ws_all, (uint32_t)ws_off0, ev, pl->n_ev, B,        \
-                                                                        (uint32_t)ldb, bt_log2)
-                        if (g.max_k <= 2)
-                            PGX_LAUNCH_TILE32(2);
-                        else if (g.max_k <= 4)
-                            PGX_LAUNCH_TILE32(4);
-                        else
-                            PGX_LAUNCH_TILE32(8);
+                    if (idx32) {
+#define PGX_LAUNCH_TILE32(MK, RT)                                                                                          \
+    k_contract_tile32<T, MK, RT><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off,   \
+                                                                            ws_all, ws_all, (uint32_t)ws_off0, ev, pl->n_ev, \
+                                                                            B, (uint32_t)ldb, bt_log2)
+                        if (g.max_k <= 2) {
+                            if (rt) PGX_LAUNCH_TILE32(2, true); else PGX_LAUNCH_TILE32(2, false);
+                        } else if (g.max_k <= 4) {
+                            if (rt) PGX_LAUNCH_TILE32(4, true); else PGX_LAUNCH_TILE32(4, false);
+                        } else {
+                            PGX_LAUNCH_TILE32(8, false);
+                        }
 #undef PGX_LAUNCH_TILE32
                     } else if (g.max_k <= 2) {
                         if (rt) PGX_LAUNCH_TILE(2, true); else PGX_LAUNCH_TILE(2, false);

@@ -109,7 +109,8 @@ class CompiledPlan:
     # ---- execution ---------------------------------------------------------------------------
     # Largest workspace a single launch sequence may ask for; bigger batches are processed in row tiles
     # (munin needs 169 MB of work tables per evidence set: 1024 sets would want 173 GB at once).
-    MAX_WORKSPACE_BYTES = 32 << 30
+    MAX_WORKSPACE_BYTES = 31 << 30  # also keeps every element index of the 32-bit-addressed step kernel below 2^32
+    MAX_ROWS_PER_PASS = 1 << 20  # the stepwise grid covers at most 65 535 tiles of 32 evidence sets
 
     def run(self, ev_states, out=None, workspace=None):
         """ev_states: int32 CUDA tensor [B, n_ev] (or [B, 0] / None with B given by `out`).
@@ -117,9 +118,10 @@ class CompiledPlan:
         torch = _torch()
         if workspace is None:
             B_all = ev_states.shape[0] if ev_states is not None else (out.shape[0] if out is not None else 0)
-            if B_all > 32 and self.workspace_bytes(B_all) > self.MAX_WORKSPACE_BYTES:
+            if B_all > 32 and (self.workspace_bytes(B_all) > self.MAX_WORKSPACE_BYTES or B_all > self.MAX_ROWS_PER_PASS):
                 per_set = self.workspace_bytes(32) // 32
                 tile = max(32, int(self.MAX_WORKSPACE_BYTES // max(per_set, 1)) // 32 * 32)
+                tile = min(tile, self.MAX_ROWS_PER_PASS)
                 if out is None:
                     out = torch.empty((B_all, self.out_elems), dtype=self.torch_dtype, device=self.device)
                 for lo in range(0, B_all, tile):

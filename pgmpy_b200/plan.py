@@ -34,6 +34,7 @@ Word pool layout (int32 words; 64-bit values as lo,hi):
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Hashable, List, Optional, Sequence, Tuple
 
@@ -155,7 +156,8 @@ class Plan:
 class PlanBuilder:
     """Collects tables and steps, then assigns workspace offsets by liveness and packs the pool."""
 
-    def __init__(self, card: Dict[Hashable, int], ev_vars: Sequence[Hashable]):
+    def __init__(self, card: Dict[Hashable, int], ev_vars: Sequence[Hashable], reassociate: bool = True):
+        self.reassociate = reassociate and os.environ.get("PGX_NO_REASSOC", "0") != "1"
         self.card = {v: int(c) for v, c in card.items()}
         self.ev_vars = tuple(ev_vars)
         self.ev_slot = {v: i for i, v in enumerate(self.ev_vars)}
@@ -241,7 +243,7 @@ class PlanBuilder:
                         sc.append(v)
             return sc
 
-        if optimize and len(ops) > 2:
+        if optimize and len(ops) > 2 and self.reassociate:
             while len(ops) > 2:
                 final_joint = self._prod(union_scope(ops))
                 count: Dict[Hashable, int] = {}

@@ -128,7 +128,8 @@ if __name__ == "__main__":
         bp_all_marginals("pathfinder", 16384)
         bp_all_marginals("diabetes", 2048)
     if what and what[0] == "one":
-        bp_all_marginals(what[1], int(what[2]), reps=int(what[3]) if len(what) > 3 else 3, reg_tile=False)
+        bp_all_marginals(what[1], int(what[2]), reps=int(what[3]) if len(what) > 3 else 3,
+                         reg_tile=bool(int(what[4])) if len(what) > 4 else False)
         sys.exit(0)
     if "rtile" in what:
         for name, b in (("pathfinder", 4096), ("diabetes", 1024), ("munin", 64)):
