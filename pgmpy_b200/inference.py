@@ -335,8 +335,39 @@ class VariableElimination(_Inference):
             flat = flat // c
         return torch.stack(cols[::-1], dim=1)
 
+    def induced_graph(self, elimination_order):
+        """Induced graph of running variable elimination in the given order (host graph code,
+        ExactInference.py:626-691): a networkx.Graph whose edges join every pair of variables that share a factor
+        at some point of the elimination."""
+        import itertools
+
+        import networkx as nx
+
+        if isinstance(self.model, JunctionTree):
+            scopes = [list(f.variables) for f in self.model.get_factors()]
+        else:
+            scopes = [list(c.variables) for c in self.model.get_cpds()]
+        if set(elimination_order) != set(self.variables):
+            raise ValueError("Set of variables in elimination order different from variables in model")
+        working = {v: [sc for sc in scopes if v in sc] for v in self.variables}
+        cliques = {tuple(sc) for sc in scopes}
+        eliminated = set()
+        for var in elimination_order:
+            factors = [f for f in working[var] if not set(f) & eliminated]
+            phi = set(itertools.chain(*factors)) - {var}
+            cliques.add(tuple(phi))
+            del working[var]
+            for v in phi:
+                working[v].append(list(phi))
+            eliminated.add(var)
+        edges = itertools.chain(*[itertools.combinations(c, 2) for c in cliques if len(c) > 1])
+        return nx.Graph(edges)
+
     def induced_width(self, elimination_order):
-        raise NotImplementedError("induced_width is outside the accelerated path")
+        """Size of the largest clique of the induced graph minus one (ExactInference.py:693-733)."""
+        import networkx as nx
+
+        return max(len(c) for c in nx.find_cliques(self.induced_graph(elimination_order))) - 1
 
 
 class BeliefPropagation(_Inference):

@@ -587,3 +587,44 @@ def test_ve_marginals_batch_single_plan_vs_reference_golden(torch_cuda, name):
     out = ve.marginals_batch(g["ev_vars"], g["ev_states"]).cpu().numpy()
     col = {s.vars[0]: (s.out_offset, s.table.size) for s in cp.plan.segments}
     assert max(rel_err(out[case, col[q][0] : col[q][0] + col[q][1]], want) for case, q, want in g["ve"]) <= 1e-12
+
+
+def test_bp_on_user_junction_tree_calibrate_and_max_calibrate(torch_cuda):
+    """BeliefPropagation(JunctionTree) with arbitrary (non-normalised, zero-containing) potentials: calibrated
+    clique / sepset beliefs equal the hand-derived factor algebra of the reference's own test
+    (pgmpy/tests/test_inference/test_ExactInference.py:891-1033); the expectation is computed with OUR
+    DiscreteFactor algebra, i.e. also on the GPU."""
+    from pgmpy_b200 import DiscreteFactor, JunctionTree
+    from pgmpy_b200.inference import BeliefPropagation
+
+    def fresh():
+        return (DiscreteFactor(["A", "B"], [2, 3], range(6)), DiscreteFactor(["B", "C"], [3, 2], range(6)),
+                DiscreteFactor(["C", "D"], [2, 2], range(4)))
+
+    jt = JunctionTree([(("A", "B"), ("B", "C")), (("B", "C"), ("C", "D"))])
+    jt.add_factors(*fresh())
+    bp = BeliefPropagation(jt)
+    bp.calibrate()
+    phi1, phi2, phi3 = fresh()
+    b_ab = phi1 * (phi3.marginalize(["D"], inplace=False) * phi2).marginalize(["C"], inplace=False)
+    b_bc = phi2 * (phi1.marginalize(["A"], inplace=False) * phi3.marginalize(["D"], inplace=False))
+    b_cd = phi3 * (phi1.marginalize(["A"], inplace=False) * phi2).marginalize(["B"], inplace=False)
+    beliefs = bp.get_clique_beliefs()
+    assert beliefs[("A", "B")] == b_ab and beliefs[("B", "C")] == b_bc and beliefs[("C", "D")] == b_cd
+    seps = bp.get_sepset_beliefs()
+    np.testing.assert_allclose(seps[frozenset((("A", "B"), ("B", "C")))].values,
+                               b_ab.marginalize(["A"], inplace=False).values, rtol=1e-13)
+    np.testing.assert_allclose(seps[frozenset((("B", "C"), ("C", "D")))].values,
+                               b_bc.marginalize(["B"], inplace=False).values, rtol=1e-13)
+    bp.max_calibrate()
+    m_ab = phi1 * (phi3.maximize(["D"], inplace=False) * phi2).maximize(["C"], inplace=False)
+    m_bc = phi2 * (phi1.maximize(["A"], inplace=False) * phi3.maximize(["D"], inplace=False))
+    m_cd = phi3 * (phi1.maximize(["A"], inplace=False) * phi2).maximize(["B"], inplace=False)
+    mb = bp.get_clique_beliefs()
+    assert mb[("A", "B")] == m_ab and mb[("B", "C")] == m_bc and mb[("C", "D")] == m_cd
+    # query on the user tree: normalised like the reference does for JunctionTree models (:416-420)
+    q = bp.query(["A"], evidence={"D": 1})
+    joint = O.factor_product(O.Factor(["A", "B"], np.arange(6.0).reshape(2, 3)), O.Factor(["B", "C"], np.arange(6.0).reshape(3, 2)),
+                             O.Factor(["C", "D"], np.arange(4.0).reshape(2, 2)))
+    want = O.normalize(O.marginalize(O.reduce(joint, [("D", 1)]), ["B", "C"]))
+    np.testing.assert_allclose(q.values, want.values, rtol=1e-13)

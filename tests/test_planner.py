@@ -212,3 +212,19 @@ def test_multi_query_ve_plan_matches_reference_golden(name):
     out = run_plan(plan.pool, plan.const_blob, g["ev_states"])
     col = {s.vars[0]: (s.out_offset, s.table.size) for s in plan.segments}
     assert max(rel_err(out[case, col[q][0] : col[q][0] + col[q][1]], want) for case, q, want in g["ve"]) <= 1e-12
+
+
+def test_induced_graph_and_width_known_answers():
+    """pgmpy/tests/test_inference/test_ExactInference.py:341-364 (host graph code; no GPU involved).
+    The constructor only needs the model, so it is built without touching the engine."""
+    from pgmpy_b200.inference import VariableElimination
+
+    ve = VariableElimination.__new__(VariableElimination)
+    ve.model = six_node_net()
+    ve.variables = set(ve.model.nodes())
+    g = ve.induced_graph(["G", "Q", "A", "J", "L", "R"])
+    assert sorted(sorted(e) for e in g.edges()) == [
+        ["A", "J"], ["A", "R"], ["G", "J"], ["G", "L"], ["J", "L"], ["J", "Q"], ["J", "R"], ["L", "R"]]
+    assert ve.induced_width(["G", "Q", "A", "J", "L", "R"]) == 2
+    with pytest.raises(ValueError):
+        ve.induced_graph(["G", "Q"])
