@@ -133,6 +133,40 @@ class Plan:
         total += 4 * batch * len(self.ev_vars) + itemsize * batch * self.out_elems
         return total
 
+    # ---- plan cache on disk: a compiled plan is two arrays + a little metadata -----------
+    def save(self, path: str) -> None:
+        """Serialise the executable part of the plan (word pool, table blob, evidence slots, output segments).
+        A loaded plan runs exactly like the original; only the planner-side step objects are not kept."""
+        import json
+
+        segs = [[list(map(str, s.vars)), int(s.out_offset), int(s.table.size), bool(s.normalize), list(map(int, s.table.dims))]
+                for s in self.segments]
+        header = {
+            "ev_vars": list(self.ev_vars), "card": {str(k): int(v) for k, v in self.card.items()},
+            "segments": segs, "out_elems": self.out_elems, "ws_entries": self.ws_entries, "n_steps": self.n_steps,
+            "meta": {k: v for k, v in self.meta.items() if isinstance(v, (str, int, float, bool))},
+            "alg_bytes_per_set": self.algorithmic_bytes(1) if self.steps else self.meta.get("alg_bytes_per_set", 0),
+        }
+        np.savez_compressed(path, pool=self.pool, const_blob=self.const_blob, header=np.array(json.dumps(header)))
+
+    @classmethod
+    def load(cls, path: str) -> "Plan":
+        import json
+
+        with np.load(path, allow_pickle=False) as z:
+            header = json.loads(str(z["header"]))
+            pool = z["pool"].astype(np.int32)
+            blob = z["const_blob"].astype(np.float64)
+        segments = []
+        for vars_, out_off, size, norm, dims in header["segments"]:
+            t = Table(KIND_WORK, tuple(vars_), tuple(dims))
+            segments.append(Segment(t, out_off, norm, tuple(vars_)))
+        meta = dict(header["meta"])
+        meta["alg_bytes_per_set"] = header["alg_bytes_per_set"]
+        return cls(pool=pool, const_blob=blob, ev_vars=tuple(header["ev_vars"]), segments=segments,
+                   out_elems=header["out_elems"], ws_entries=header["ws_entries"], n_steps=header["n_steps"],
+                   card=header["card"], steps=[], meta=meta)
+
     def operand_loads(self) -> int:
         """Operand loads (= multiplies) per evidence set: sum over steps of |out| * |sum| * #operands."""
         total = 0

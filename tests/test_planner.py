@@ -228,3 +228,20 @@ def test_induced_graph_and_width_known_answers():
     assert ve.induced_width(["G", "Q", "A", "J", "L", "R"]) == 2
     with pytest.raises(ValueError):
         ve.induced_graph(["G", "Q"])
+
+
+def test_plan_save_load_round_trip(tmp_path):
+    """A plan written to disk and read back executes identically (plan cache)."""
+    from pgmpy_b200.plan import Plan
+
+    m = px.get_example_model("alarm")
+    ev_vars, states = sample_evidence(m, 7, 5, seed=8)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars)
+    path = str(tmp_path / "alarm_plan.npz")
+    plan.save(path)
+    back = Plan.load(path)
+    assert np.array_equal(back.pool, plan.pool) and np.array_equal(back.const_blob, plan.const_blob)
+    assert list(back.ev_vars) == list(plan.ev_vars) and back.out_elems == plan.out_elems
+    assert [(s.vars, s.out_offset, s.table.size) for s in back.segments] == [(tuple(map(str, s.vars)), s.out_offset, s.table.size) for s in plan.segments]
+    np.testing.assert_array_equal(run_plan(back.pool, back.const_blob, states), run_plan(plan.pool, plan.const_blob, states))
+    np.testing.assert_array_equal(hostsim_run(back, states), hostsim_run(plan, states))
