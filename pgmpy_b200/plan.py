@@ -120,6 +120,8 @@ class Plan:
     def algorithmic_bytes(self, batch: int, itemsize: int = 8) -> int:
         """every tensor counted once per step in which it is an operand or result,
         batch-invariant operands once per step, plus evidence in and posteriors out."""
+        if not self.steps and self.meta.get("alg_bytes_per_set"):
+            return int(self.meta["alg_bytes_per_set"]) * batch  # plan loaded from the cache: figure stored per set
         total = 0
         for st in self.steps:
             work = st.out.size
