@@ -445,6 +445,22 @@ def compile_jt_plan(
         lvl = base_level + 2 * jt.depth[i]
         if want_belief(i):
             belief[i] = b.contract([psi[i]] + incoming(i), free[i], level=lvl)
+        if i in belief and fsize(free[i]) >= 4096 and len(jt.children[i]) >= 2:
+            # big belief, several children: marginalisation lattice. Child sepsets are served largest first, each from
+            # the smallest table already summed whose scope contains it (sum_{C \ S_a} = sum_{S_b \ S_a} sum_{C \ S_b}
+            # when S_a is inside S_b), so a 2.7 M-entry munin belief is swept once or twice instead of once per
+            # child; the sigma / mu division (0/0 -> 0) is applied to the small result.
+            done: List[Tuple[Tuple[Hashable, ...], Table]] = []
+            for c in sorted(jt.children[i], key=lambda c: -fsize(sep(i, c))):
+                s_c = sep(i, c)
+                src = belief[i]
+                for scope, tab in done:
+                    if set(s_c) <= set(scope) and tab.size < src.size:
+                        src = tab
+                undivided = b.contract([src], s_c, level=lvl + 1, reduce_max=reduce_max)
+                done.append((s_c, undivided))
+                down[c] = b.contract([undivided], s_c, divisors=[up[c]], level=lvl + 1, reduce_max=reduce_max)
+            continue
         for c in jt.children[i]:
             if i in belief:
                 down[c] = b.contract([belief[i]], sep(i, c), divisors=[up[c]], level=lvl + 1, reduce_max=reduce_max)
