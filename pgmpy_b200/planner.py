@@ -451,6 +451,12 @@ def compile_jt_plan(
             # when S_a is inside S_b), so a 2.7 M-entry munin belief is swept once or twice instead of once per
             # child; the sigma / mu division (0/0 -> 0) is applied to the small result.
             done: List[Tuple[Tuple[Hashable, ...], Table]] = []
+            union = [v for v in free[i] if any(v in jt.cliques[c] for c in jt.children[i])]
+            biggest = max(fsize(sep(i, c)) for c in jt.children[i])
+            if biggest < fsize(union) <= fsize(free[i]) // 4:
+                # no child sepset contains the others, but together they span only part of the clique: sum the
+                # belief down to that union once, then serve every child from the smaller table
+                done.append((tuple(union), b.contract([belief[i]], union, level=lvl + 1, reduce_max=reduce_max)))
             for c in sorted(jt.children[i], key=lambda c: -fsize(sep(i, c))):
                 s_c = sep(i, c)
                 src = belief[i]
