@@ -68,6 +68,8 @@ extern "C" {
 
 #define PGX_OPT_REG_TILE 6     /* stepwise mode: register-tile GEMM-shaped steps (default 0: measured neutral) */
 
+#define PGX_OPT_GEMM_TILE 7    /* stepwise mode: 2-D register-tiled kernel for GEMM-shaped steps (default 1) */
+
 #define PGX_INFO_N_STEPS 1
 #define PGX_INFO_OUT_ELEMS 2
 #define PGX_INFO_WS_ENTRIES 3

@@ -584,6 +584,250 @@ __global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ?
     }
 }
 
+// K3 — GEMM-shaped steps (two or three operands sharing the summed variables, each depending on only part of the
+// output scope; diabetes, parts of pathfinder/munin). Same launch contract and phase 1 as k_contract_tile32; in phase 2
+// a thread owns an R2 x R1 block of the output seen as a matrix [slower axes][fastest axis] and keeps R2*R1
+// accumulators in registers. Inside such a block an operand's entry offset is separable,
+//     e(r2, r1) = e00 + d2[r2] + d1[r1],
+// and an operand that does not contain the fastest output variable has d1 == 0 (one row per r2 serves R1 outputs),
+// one that does not contain the next-slower variable has d2 == 0. Per summed index the thread therefore loads
+// R2 + R1 rows of the two small operands instead of 2*R2*R1 — the reuse a GEMM tile gets from registers — which cuts
+// the L2->L1 re-reads that bound these steps. fp64 has no tcgen05 kind and DMMA peaks where DFMA does on B200, and the
+// fp64 pipe is < 10 % busy here, so the tile is fed by plain DFMA.
+template <typename T, int MAXK>
+__global__ void __launch_bounds__(256, 3) k_contract_gemm32(const int32_t* __restrict__ pool,
+                                                            const TileItem* __restrict__ items, int n_items,
+                                                            int ev_card_off, const T* __restrict__ ws_in,
+                                                            T* __restrict__ ws_out, uint32_t ws_off0,
+                                                            const int32_t* __restrict__ ev, int n_ev, int64_t B,
+                                                            uint32_t ldb) {
+    constexpr int R1 = 3, R2 = 3;
+    extern __shared__ int32_t s_mem[];
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (items[mid].blk_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const TileItem it = items[lo];
+    const int local = (int)blockIdx.x - it.blk_begin;
+    const int tile_x = local / it.b_blocks;
+    const int b_block = local - tile_x * it.b_blocks;
+    const int TO = it.TO, btb = it.btb, rec_len = it.rec_len;
+
+    int32_t* s_rec = s_mem;
+    for (int i = threadIdx.x; i < rec_len; i += blockDim.x) s_rec[i] = pool[it.rec_off + i];
+    __syncthreads();
+    const int A = s_rec[0], S = s_rec[1], K = s_rec[2];
+    const int opw = OP_FIXED + A + S;
+    const int32_t* odims = s_rec + STEP_FIXED;
+    const int32_t* sdims = odims + A;
+    const int32_t* ops = sdims + S;
+    const uint32_t out_size = (uint32_t)s_rec[4];
+    const int sum_size = s_rec[6];
+    int32_t* s_otab = s_mem + ((rec_len + 3) & ~3);
+    int32_t* s_stab = s_otab + TO * K;
+    const uint32_t tile0 = (uint32_t)tile_x * (uint32_t)TO;
+    for (int t = threadIdx.x; t < TO; t += blockDim.x) {
+        uint32_t rem = tile0 + t;
+        int32_t off[MAXK];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) off[k] = 0;
+        if (rem < out_size) {
+            for (int a = A - 1; a >= 0; --a) {
+                const uint32_t d = (uint32_t)odims[a];
+                const uint32_t q = rem / d;
+                const int32_t digit = (int32_t)(rem - q * d);
+                rem = q;
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k)
+                    if (k < K) off[k] += digit * ops[k * opw + OP_FIXED + a];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+            if (k < K) s_otab[t * K + k] = off[k];
+    }
+    for (int qi = threadIdx.x; qi < sum_size; qi += blockDim.x) {
+        uint32_t rem = (uint32_t)qi;
+        int32_t off[MAXK];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) off[k] = 0;
+        for (int a = S - 1; a >= 0; --a) {
+            const uint32_t d = (uint32_t)sdims[a];
+            const uint32_t q = rem / d;
+            const int32_t digit = (int32_t)(rem - q * d);
+            rem = q;
+#pragma unroll
+            for (int k = 0; k < MAXK; ++k)
+                if (k < K) off[k] += digit * ops[k * opw + OP_FIXED + A + a];
+        }
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+            if (k < K) s_stab[qi * K + k] = off[k];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int n1 = odims[A - 1];                 // fastest output axis (host guarantees A >= 1 and TO % n1 == 0)
+    const int rows_in_tile = TO / n1;
+    const int col_blocks = (n1 + R1 - 1) / R1;
+    const int row_blocks = (rows_in_tile + R2 - 1) / R2;
+    const uint32_t out_base = ws_off0 + (uint32_t)s_rec[8] * ldb;
+    const int32_t* ev_card = pool + ev_card_off;
+    for (int tb = 0; tb < btb; ++tb) {
+        const int64_t b = ((int64_t)b_block * btb + tb) * 32 + lane;
+        if (b >= B) continue;  // no barriers below
+        uint32_t rowb[MAXK], unit[MAXK];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) {
+            rowb[k] = 0;
+            unit[k] = 0;
+            if (k < K) {
+                const int32_t* op = ops + k * opw;
+                uint32_t e = (uint32_t)op[1];
+                const int ne = op[3];
+                if (ne > 0) {
+                    const int32_t* pairs = s_rec + op[4];
+                    for (int j = 0; j < ne; ++j) {
+                        const int slot = pairs[2 * j];
+                        int32_t st = ev[b * n_ev + slot];
+                        const int32_t card = ev_card[slot];
+                        st = st < 0 ? 0 : (st >= card ? card - 1 : st);
+                        e += (uint32_t)(st * pairs[2 * j + 1]);
+                    }
+                }
+                if ((op[0] & 0xFF) == 1) {
+                    unit[k] = ldb;
+                    rowb[k] = ws_off0 + e * ldb + (uint32_t)b;
+                } else {
+                    unit[k] = 1;
+                    rowb[k] = e;
+                }
+            }
+        }
+        const uint32_t outb = out_base + (uint32_t)b;
+        for (int blk = warp; blk < row_blocks * col_blocks; blk += n_warps) {
+            const int rb = blk / col_blocks, cb = blk - rb * col_blocks;
+            const int r0 = rb * R2, c0 = cb * R1;
+            const uint32_t o00 = tile0 + (uint32_t)(r0 * n1 + c0);
+            if (o00 >= out_size) continue;
+            int nr2 = rows_in_tile - r0 < R2 ? rows_in_tile - r0 : R2;
+            const int rows_left = (int)((out_size - (tile0 + (uint32_t)(r0 * n1))) / (uint32_t)n1);
+            if (nr2 > rows_left) nr2 = rows_left;
+            const int nc = n1 - c0 < R1 ? n1 - c0 : R1;
+            // separable offsets of every operand inside the block (checked: any deviation -> entry-by-entry path)
+            uint32_t e00[MAXK], d1[MAXK][R1], d2[MAXK][R2];
+            bool separable = true;
+#pragma unroll
+            for (int k = 0; k < MAXK; ++k) {
+                e00[k] = 0;
+#pragma unroll
+                for (int r = 0; r < R1; ++r) d1[k][r] = 0;
+#pragma unroll
+                for (int r = 0; r < R2; ++r) d2[k][r] = 0;
+                if (k < K) {
+                    const int32_t base = s_otab[(r0 * n1 + c0) * K + k];
+                    e00[k] = rowb[k] + (uint32_t)base * unit[k];
+#pragma unroll
+                    for (int r = 1; r < R1; ++r)
+                        if (r < nc) d1[k][r] = (uint32_t)(s_otab[(r0 * n1 + c0 + r) * K + k] - base) * unit[k];
+#pragma unroll
+                    for (int r = 1; r < R2; ++r)
+                        if (r < nr2) d2[k][r] = (uint32_t)(s_otab[((r0 + r) * n1 + c0) * K + k] - base) * unit[k];
+#pragma unroll
+                    for (int r2 = 1; r2 < R2; ++r2)
+#pragma unroll
+                        for (int r1 = 1; r1 < R1; ++r1)
+                            if (r2 < nr2 && r1 < nc &&
+                                (uint32_t)(s_otab[((r0 + r2) * n1 + c0 + r1) * K + k] - base) * unit[k] != d1[k][r1] + d2[k][r2])
+                                separable = false;
+                }
+            }
+            if (!separable) {
+                for (int r2 = 0; r2 < nr2; ++r2)
+                    for (int r1 = 0; r1 < nc; ++r1) {
+                        const int og = (r0 + r2) * n1 + c0 + r1;
+                        T acc = (T)0;
+                        const int32_t* st = s_stab;
+                        for (int q = 0; q < sum_size; ++q, st += K) {
+                            T prod = (T)1;
+#pragma unroll
+                            for (int k = 0; k < MAXK; ++k)
+                                if (k < K) prod *= ws_in[rowb[k] + (uint32_t)(s_otab[og * K + k] + st[k]) * unit[k]];
+                            acc += prod;
+                        }
+                        ws_out[outb + (tile0 + (uint32_t)og) * ldb] = acc;
+                    }
+                continue;
+            }
+            bool dep1[MAXK], dep2[MAXK];
+#pragma unroll
+            for (int k = 0; k < MAXK; ++k) {
+                dep1[k] = false;
+                dep2[k] = false;
+#pragma unroll
+                for (int r = 1; r < R1; ++r) dep1[k] = dep1[k] || d1[k][r] != 0;
+#pragma unroll
+                for (int r = 1; r < R2; ++r) dep2[k] = dep2[k] || d2[k][r] != 0;
+            }
+            T acc[R2][R1];
+#pragma unroll
+            for (int r2 = 0; r2 < R2; ++r2)
+#pragma unroll
+                for (int r1 = 0; r1 < R1; ++r1) acc[r2][r1] = (T)0;
+            const int32_t* st = s_stab;
+            for (int q = 0; q < sum_size; ++q, st += K) {
+                T prod[R2][R1];
+#pragma unroll
+                for (int r2 = 0; r2 < R2; ++r2)
+#pragma unroll
+                    for (int r1 = 0; r1 < R1; ++r1) prod[r2][r1] = (T)1;
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k) {
+                    if (k < K) {
+                        const uint32_t a0 = e00[k] + (uint32_t)st[k] * unit[k];
+                        if (dep1[k] && dep2[k]) {
+#pragma unroll
+                            for (int r2 = 0; r2 < R2; ++r2)
+#pragma unroll
+                                for (int r1 = 0; r1 < R1; ++r1) prod[r2][r1] *= ws_in[a0 + d2[k][r2] + d1[k][r1]];
+                        } else if (dep2[k]) {
+#pragma unroll
+                            for (int r2 = 0; r2 < R2; ++r2) {
+                                const T v = ws_in[a0 + d2[k][r2]];
+#pragma unroll
+                                for (int r1 = 0; r1 < R1; ++r1) prod[r2][r1] *= v;
+                            }
+                        } else if (dep1[k]) {
+#pragma unroll
+                            for (int r1 = 0; r1 < R1; ++r1) {
+                                const T v = ws_in[a0 + d1[k][r1]];
+#pragma unroll
+                                for (int r2 = 0; r2 < R2; ++r2) prod[r2][r1] *= v;
+                            }
+                        } else {
+                            const T v = ws_in[a0];
+#pragma unroll
+                            for (int r2 = 0; r2 < R2; ++r2)
+#pragma unroll
+                                for (int r1 = 0; r1 < R1; ++r1) prod[r2][r1] *= v;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r2 = 0; r2 < R2; ++r2)
+#pragma unroll
+                    for (int r1 = 0; r1 < R1; ++r1) acc[r2][r1] += prod[r2][r1];
+            }
+#pragma unroll
+            for (int r2 = 0; r2 < R2; ++r2)
+#pragma unroll
+                for (int r1 = 0; r1 < R1; ++r1)
+                    if (r2 < nr2 && r1 < nc) ws_out[outb + (o00 + (uint32_t)(r2 * n1 + r1)) * ldb] = acc[r2][r1];
+        }
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ void emit_segment(const int32_t* __restrict__ seg, const T* __restrict__ ws,
                                              T* __restrict__ out, int64_t out_elems, int64_t ldb, int64_t b) {
@@ -721,6 +965,7 @@ struct LaunchGroup {
     int first_item = 0, n_items = 0, n_blocks = 0, max_k = 0;
     size_t smem = 0;
     bool rtile = false;  // the group holds GEMM-shaped steps: use the register-tiled instantiation
+    bool gemm = false;   // every step of the group goes to k_contract_gemm32 (2-D register tile)
 };
 
 struct StepSchedule {
@@ -763,6 +1008,7 @@ struct pgx_plan {
     std::vector<StepSchedule> schedules;
     cudaStream_t cap_stream = nullptr;
     int last_graph = 0;
+    int gemm_tile = 1;    // route GEMM-shaped steps to k_contract_gemm32 (PGX_OPT_GEMM_TILE)
     int reg_tile = 0;     // register-tile GEMM-shaped steps (PGX_OPT_REG_TILE); measured neutral-to-slower, off by default
     int batch_levels = 1; // share one launch among the tile-eligible steps of a dependency level
     cudaEvent_t* prof_events = nullptr;  // set only inside pgx_profile_steps
@@ -964,8 +1210,9 @@ int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
         case PGX_OPT_USE_GRAPH:
             plan->use_graph = value ? 1 : 0;
             return PGX_OK;
+        case PGX_OPT_GEMM_TILE:
         case PGX_OPT_REG_TILE:
-            plan->reg_tile = value ? 1 : 0;
+            if (option == PGX_OPT_GEMM_TILE) plan->gemm_tile = value ? 1 : 0; else plan->reg_tile = value ? 1 : 0;
             for (StepSchedule& c : plan->schedules)
                 if (c.d_items) cudaFree(c.d_items);
             plan->schedules.clear();
@@ -1095,11 +1342,11 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
         // launch schedule for this batch size: tile-eligible steps of one dependency level share a launch
         StepSchedule* sched = nullptr;
         for (StepSchedule& c : pl->schedules)
-            if (c.B == B && c.step_kernel == pl->step_kernel + 2 * pl->batch_levels && c.dtype_size == (int)sizeof(T)) sched = &c;
+            if (c.B == B && c.step_kernel == pl->step_kernel + 4 * pl->batch_levels + 8 * pl->gemm_tile && c.dtype_size == (int)sizeof(T)) sched = &c;
         if (!sched) {
             StepSchedule ns;
             ns.B = B;
-            ns.step_kernel = pl->step_kernel + 2 * pl->batch_levels;
+            ns.step_kernel = pl->step_kernel + 4 * pl->batch_levels + 8 * pl->gemm_tile;
             ns.dtype_size = (int)sizeof(T);
             std::vector<TileItem> items;
             const int o_per_warp = 32 >> bt_log2;
@@ -1113,7 +1360,15 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                 const StepInfo& s = pl->steps[si];
                 const int64_t stab_words = s.sum_size * s.n_ops;
                 const bool tile_ok = s.n_ops <= 8 && stab_words <= 8192 && pl->step_kernel != 1;  // 0 tile32, 2 tile64
-                if (!tile_ok || s.level != cur_level || !pl->batch_levels) flush(cur);
+                // GEMM-shaped: a summed range worth tiling, 2..4 plain operands, a fastest output axis of >= 2 entries
+                // and at least 3 rows of it; such steps form their own launch groups (k_contract_gemm32)
+                const int32_t* srec = pl->pool.data() + s.rec_off;
+                const int sA = srec[0];
+                const int n1 = sA > 0 ? srec[STEP_FIXED + sA - 1] : 1;
+                const bool gemm_ok = tile_ok && pl->gemm_tile && bt_log2 == 5 && srec[3] == 0 && s.n_ops >= 2 && s.n_ops <= 4 &&
+                                     s.sum_size >= 8 && sA >= 2 && n1 >= 2 && n1 <= 128 && s.out_size / n1 >= 3 &&
+                                     s.out_size * s.sum_size >= 4096;
+                if (!tile_ok || s.level != cur_level || !pl->batch_levels || (cur.n_items > 0 && cur.gemm != gemm_ok)) flush(cur);
                 cur_level = s.level;
                 if (!tile_ok) {
                     LaunchGroup g;
@@ -1135,10 +1390,17 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                 if (TO * s.n_ops > 2048) TO = 2048 / s.n_ops;
                 TO = (TO + o_per_warp - 1) / o_per_warp * o_per_warp;
                 if (TO > s.out_size) TO = (s.out_size + o_per_warp - 1) / o_per_warp * o_per_warp;
+                if (gemm_ok) {
+                    // whole rows of the fastest axis, a multiple of 3 of them, ~24 row-blocks x col-blocks per CTA
+                    int64_t rows = std::max<int64_t>(3, (TO / n1) / 3 * 3);
+                    while (rows > 3 && rows * n1 * s.n_ops > 2048) rows -= 3;
+                    TO = rows * n1;
+                }
                 const int64_t n_blocks = ((s.out_size + TO - 1) / TO) * b_blocks;
                 if (cur.n_items > 0 && (int64_t)cur.n_blocks + n_blocks > (1LL << 30)) flush(cur);
                 if (cur.n_items == 0) cur.first_item = (int)items.size();
                 items.push_back(TileItem{s.rec_off, s.rec_len, (int32_t)TO, btb, (int32_t)b_blocks, (int32_t)cur.n_blocks});
+                cur.gemm = gemm_ok;
                 cur.n_items += 1;
                 cur.n_blocks += (int)n_blocks;
                 cur.max_k = std::max(cur.max_k, s.n_ops);
@@ -1194,7 +1456,16 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
     k_contract_tile<T, MK, RT><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off, cst, \
                                                                           ws, ws, ev, pl->n_ev, B, ldb, bt_log2)
                     const bool rt = g.rtile && pl->reg_tile && bt_log2 == 5;
-                    if (idx32) {
+                    if (idx32 && g.gemm) {
+                        if (g.max_k <= 2)
+                            k_contract_gemm32<T, 2><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(
+                                pl->d_pool, d_it, g.n_items, pl->ev_card_off, ws_all, ws_all, (uint32_t)ws_off0, ev, pl->n_ev, B,
+                                (uint32_t)ldb);
+                        else
+                            k_contract_gemm32<T, 4><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(
+                                pl->d_pool, d_it, g.n_items, pl->ev_card_off, ws_all, ws_all, (uint32_t)ws_off0, ev, pl->n_ev, B,
+                                (uint32_t)ldb);
+                    } else if (idx32) {
 #define PGX_LAUNCH_TILE32(MK, RT)                                                                                          \
     k_contract_tile32<T, MK, RT><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off,   \
                                                                             ws_all, ws_all, (uint32_t)ws_off0, ev, pl->n_ev, \

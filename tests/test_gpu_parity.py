@@ -628,3 +628,23 @@ def test_bp_on_user_junction_tree_calibrate_and_max_calibrate(torch_cuda):
                              O.Factor(["C", "D"], np.arange(4.0).reshape(2, 2)))
     want = O.normalize(O.marginalize(O.reduce(joint, [("D", 1)]), ["B", "C"]))
     np.testing.assert_allclose(q.values, want.values, rtol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["diabetes", "pathfinder", "hepar2"])
+def test_gemm_shaped_step_kernel_matches(torch_cuda, name):
+    """k_contract_gemm32 (2-D register tile for GEMM-shaped steps) vs the plain tile kernel and the oracle."""
+    torch = torch_cuda
+    m = px.get_example_model(name)
+    B = 70  # three tiles of 32 evidence sets, the last one ragged
+    ev_vars, states = sample_evidence(m, B, 8, seed=13)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars)
+    cp = _engine()(plan)
+    cp.set_mode("stepwise")
+    ev = torch.from_numpy(states).cuda()
+    cp.set_gemm_tile(False)
+    plain = cp.run(ev).clone()
+    cp.set_gemm_tile(True)
+    tiled = cp.run(ev)
+    assert float(((tiled - plain).abs() / plain.abs().clamp_min(1e-300)).max()) <= 1e-13
+    want = run_plan(plan.pool, plan.const_blob, states[:3])
+    assert rel_err(tiled[:3].cpu().numpy(), want) <= 1e-12
