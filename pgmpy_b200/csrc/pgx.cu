@@ -1350,12 +1350,24 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
             ns.dtype_size = (int)sizeof(T);
             std::vector<TileItem> items;
             const int o_per_warp = 32 >> bt_log2;
+            std::vector<TileItem> pending[2];  // items of the open plain / GEMM-shaped group of the current level
             auto flush = [&](LaunchGroup& g) {
-                if (g.n_items > 0) ns.groups.push_back(g);
+                if (g.n_items > 0) {
+                    std::vector<TileItem>& pv = pending[g.gemm ? 1 : 0];
+                    g.first_item = (int)items.size();
+                    items.insert(items.end(), pv.begin(), pv.end());
+                    pv.clear();
+                    ns.groups.push_back(g);
+                }
                 g = LaunchGroup();
             };
-            LaunchGroup cur;
+            // per dependency level: one group of plain tile steps, one group of GEMM-shaped steps, generic steps alone
+            LaunchGroup cur[2];
             int cur_level = -1;
+            auto flush_level = [&]() {
+                flush(cur[0]);
+                flush(cur[1]);
+            };
             for (size_t si = 0; si < pl->steps.size(); ++si) {
                 const StepInfo& s = pl->steps[si];
                 const int64_t stab_words = s.sum_size * s.n_ops;
@@ -1365,12 +1377,13 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                 const int32_t* srec = pl->pool.data() + s.rec_off;
                 const int sA = srec[0];
                 const int n1 = sA > 0 ? srec[STEP_FIXED + sA - 1] : 1;
-                const bool gemm_ok = tile_ok && pl->gemm_tile && bt_log2 == 5 && srec[3] == 0 && s.n_ops >= 2 && s.n_ops <= 4 &&
-                                     s.sum_size >= 8 && sA >= 2 && n1 >= 2 && n1 <= 128 && s.out_size / n1 >= 3 &&
-                                     s.out_size * s.sum_size >= 4096;
-                if (!tile_ok || s.level != cur_level || !pl->batch_levels || (cur.n_items > 0 && cur.gemm != gemm_ok)) flush(cur);
+                const bool gemm_ok = tile_ok && pl->gemm_tile && pl->step_kernel == 0 && bt_log2 == 5 && srec[3] == 0 &&
+                                     s.n_ops >= 2 && s.n_ops <= 4 && s.sum_size >= 8 && sA >= 2 && n1 >= 2 && n1 <= 128 &&
+                                     s.out_size / n1 >= 3 && s.out_size * s.sum_size >= 4096;
+                if (s.level != cur_level || !pl->batch_levels) flush_level();
                 cur_level = s.level;
                 if (!tile_ok) {
+                    flush_level();
                     LaunchGroup g;
                     g.generic_step = (int)si;
                     g.n_items = 1;
@@ -1391,23 +1404,23 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                 TO = (TO + o_per_warp - 1) / o_per_warp * o_per_warp;
                 if (TO > s.out_size) TO = (s.out_size + o_per_warp - 1) / o_per_warp * o_per_warp;
                 if (gemm_ok) {
-                    // whole rows of the fastest axis, a multiple of 3 of them, ~24 row-blocks x col-blocks per CTA
+                    // whole rows of the fastest axis, a multiple of 3 of them
                     int64_t rows = std::max<int64_t>(3, (TO / n1) / 3 * 3);
                     while (rows > 3 && rows * n1 * s.n_ops > 2048) rows -= 3;
                     TO = rows * n1;
                 }
+                LaunchGroup& cg = cur[gemm_ok ? 1 : 0];
                 const int64_t n_blocks = ((s.out_size + TO - 1) / TO) * b_blocks;
-                if (cur.n_items > 0 && (int64_t)cur.n_blocks + n_blocks > (1LL << 30)) flush(cur);
-                if (cur.n_items == 0) cur.first_item = (int)items.size();
-                items.push_back(TileItem{s.rec_off, s.rec_len, (int32_t)TO, btb, (int32_t)b_blocks, (int32_t)cur.n_blocks});
-                cur.gemm = gemm_ok;
-                cur.n_items += 1;
-                cur.n_blocks += (int)n_blocks;
-                cur.max_k = std::max(cur.max_k, s.n_ops);
-                if (s.sum_size >= 4 && s.n_ops >= 2 && s.out_size >= 64) cur.rtile = true;
-                cur.smem = std::max(cur.smem, (size_t)(((s.rec_len + 3) & ~3) + TO * s.n_ops + stab_words) * sizeof(int32_t));
+                if (cg.n_items > 0 && (int64_t)cg.n_blocks + n_blocks > (1LL << 30)) flush(cg);
+                pending[gemm_ok ? 1 : 0].push_back(TileItem{s.rec_off, s.rec_len, (int32_t)TO, btb, (int32_t)b_blocks, (int32_t)cg.n_blocks});
+                cg.gemm = gemm_ok;
+                cg.n_items += 1;
+                cg.n_blocks += (int)n_blocks;
+                cg.max_k = std::max(cg.max_k, s.n_ops);
+                if (s.sum_size >= 4 && s.n_ops >= 2 && s.out_size >= 64) cg.rtile = true;
+                cg.smem = std::max(cg.smem, (size_t)(((s.rec_len + 3) & ~3) + TO * s.n_ops + stab_words) * sizeof(int32_t));
             }
-            flush(cur);
+            flush_level();
             if (!items.empty()) {
                 PGX_CUDA(cudaMalloc((void**)&ns.d_items, items.size() * sizeof(TileItem)));
                 PGX_CUDA(cudaMemcpy(ns.d_items, items.data(), items.size() * sizeof(TileItem), cudaMemcpyHostToDevice));
