@@ -68,7 +68,7 @@ extern "C" {
 
 #define PGX_OPT_REG_TILE 6     /* stepwise mode: register-tile GEMM-shaped steps (default 0: measured neutral) */
 
-#define PGX_OPT_GEMM_TILE 7    /* stepwise mode: 2-D register-tiled kernel for GEMM-shaped steps (default 1) */
+#define PGX_OPT_GEMM_TILE 7    /* stepwise mode: 2-D register-tiled kernel for GEMM-shaped steps (default 0: measured slower) */
 
 #define PGX_INFO_N_STEPS 1
 #define PGX_INFO_OUT_ELEMS 2
