@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ?
         }
 #pragma unroll
         for (int k = 0; k < MAXK; ++k)
-            if (k < K) s_otab[t * K + k] = (int32_t)((uint32_t)off[k] * (((ops[k * opw] & 0xFF) == 1) ? ldb : 1u));
+            if (k < K) s_otab[t * K + k] = off[k];
     }
     for (int qi = threadIdx.x; qi < sum_size; qi += blockDim.x) {
         uint32_t rem = (uint32_t)qi;
@@ -419,9 +419,9 @@ __global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ?
         }
 #pragma unroll
         for (int k = 0; k < MAXK; ++k)
-            if (k < K) s_stab[qi * K + k] = (int32_t)((uint32_t)off[k] * (((ops[k * opw] & 0xFF) == 1) ? ldb : 1u));
+            if (k < K) s_stab[qi * K + k] = off[k];
     }
-    __syncthreads();  // the offset tables now hold ELEMENT offsets (entry offset x elements per entry)
+    __syncthreads();
 
     int n_mul = K;
     if (flags & FLAG_DIV)
@@ -437,10 +437,11 @@ __global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ?
     for (int tb = 0; tb < btb; ++tb) {
         const int64_t b = ((int64_t)b_block * btb + tb) * bt + (lane & (bt - 1));
         if (b >= B) continue;  // no barriers below
-        uint32_t rowb[MAXK];
+        uint32_t rowb[MAXK], unit[MAXK];
 #pragma unroll
         for (int k = 0; k < MAXK; ++k) {
             rowb[k] = 0;
+            unit[k] = 0;
             if (k < K) {
                 const int32_t* op = ops + k * opw;
                 uint32_t e = (uint32_t)op[1];
@@ -455,7 +456,13 @@ __global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ?
                         e += (uint32_t)(st * pairs[2 * j + 1]);
                     }
                 }
-                rowb[k] = ((op[0] & 0xFF) == 1) ? ws_off0 + e * ldb + (uint32_t)b : e;
+                if ((op[0] & 0xFF) == 1) {
+                    unit[k] = ldb;
+                    rowb[k] = ws_off0 + e * ldb + (uint32_t)b;
+                } else {
+                    unit[k] = 1;
+                    rowb[k] = e;
+                }
             }
         }
         const uint32_t outb = out_base + (uint32_t)b;
@@ -470,8 +477,8 @@ __global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ?
 #pragma unroll
                 for (int k = 0; k < MAXK; ++k) {
                     if (k < K) {
-                        const T v0 = ws_in[rowb[k] + (uint32_t)ot0[k]];
-                        const T v1 = ws_in[rowb[k] + (uint32_t)ot1[k]];
+                        const T v0 = ws_in[rowb[k] + (uint32_t)ot0[k] * unit[k]];
+                        const T v1 = ws_in[rowb[k] + (uint32_t)ot1[k] * unit[k]];
                         p0 *= v0;
                         p1 *= v1;
                     }
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ?
 #pragma unroll
                     for (int r = 0; r < RT; ++r) {
                         const int rr = r < nr ? r : 0;
-                        p[r][k] = (k < K) ? rowb[k] + (uint32_t)s_otab[(og + rr) * K + k] : 0;
+                        p[r][k] = (k < K) ? rowb[k] + (uint32_t)s_otab[(og + rr) * K + k] * unit[k] : 0;
                         if (p[r][k] != p[0][k]) same[k] = false;
                     }
                 }
@@ -515,7 +522,7 @@ __global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ?
 #pragma unroll
                     for (int k = 0; k < MAXK; ++k) {
                         if (k < K) {
-                            const uint32_t so = (uint32_t)st[k];
+                            const uint32_t so = (uint32_t)st[k] * unit[k];
                             if (same[k]) {
                                 const T v = ws_in[p[0][k] + so];
 #pragma unroll
@@ -541,7 +548,7 @@ __global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ?
             const int32_t* ot = s_otab + og * K;
             uint32_t p[MAXK];
 #pragma unroll
-            for (int k = 0; k < MAXK; ++k) p[k] = (k < K) ? rowb[k] + (uint32_t)ot[k] : 0;
+            for (int k = 0; k < MAXK; ++k) p[k] = (k < K) ? rowb[k] + (uint32_t)ot[k] * unit[k] : 0;
             T acc;
             if (S == 0) {
                 T prod = (T)1;
@@ -557,7 +564,7 @@ __global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ?
                     T prod = (T)1;
 #pragma unroll
                     for (int k = 0; k < MAXK; ++k)
-                        if (k < n_mul) prod *= ws_in[p[k] + (uint32_t)st[k]];
+                        if (k < n_mul) prod *= ws_in[p[k] + (uint32_t)st[k] * unit[k]];
                     if (use_max)
                         acc = prod > acc ? prod : acc;
                     else
