@@ -43,6 +43,9 @@ int fail(int code, const std::string& msg) {
 
 using namespace pgx;
 
+#ifndef PGX_TILE32V_MINB
+#define PGX_TILE32V_MINB 6  // CTAs per SM for the two-evidence-sets-per-lane tile kernel
+#endif
 #ifndef PGX_TILE32_RT_MINB
 #define PGX_TILE32_RT_MINB 4  // CTAs per SM for the register-tiled instantiation of the 32-bit tile kernel
 #endif
@@ -584,6 +587,216 @@ __global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ?
     }
 }
 
+// 16-byte lanes: the same kernel as k_contract_tile32 with TWO evidence sets per lane (b, b+1 — adjacent in the
+// [entry][ldb] layout, so a work-table operand is one 16-byte load and a warp covers 64 evidence sets = a 512-byte row
+// segment). Halves the address arithmetic, offset-table reads and load/store instructions per element and doubles the
+// bytes in flight per warp. Batch-invariant operands are scalar loads: one if the operand has no observed axis, else
+// one per evidence set.
+template <typename T> struct Pair;
+template <> struct Pair<double> { using type = double2; };
+template <> struct Pair<float> { using type = float2; };
+
+template <typename T, int MAXK>
+__global__ void __launch_bounds__(256, MAXK <= 4 ? PGX_TILE32V_MINB : 2) k_contract_tile32v(
+    const int32_t* __restrict__ pool, const TileItem* __restrict__ items, int n_items, int ev_card_off,
+    const T* __restrict__ ws_in, T* __restrict__ ws_out, uint32_t ws_off0, const int32_t* __restrict__ ev, int n_ev, int64_t B,
+    uint32_t ldb) {
+    using V = typename Pair<T>::type;
+    extern __shared__ int32_t s_mem[];
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (items[mid].blk_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const TileItem it = items[lo];
+    const int local = (int)blockIdx.x - it.blk_begin;
+    const int tile_x = local / it.b_blocks;
+    const int b_block = local - tile_x * it.b_blocks;
+    const int TO = it.TO, btb = it.btb, rec_len = it.rec_len;
+
+    int32_t* s_rec = s_mem;
+    for (int i = threadIdx.x; i < rec_len; i += blockDim.x) s_rec[i] = pool[it.rec_off + i];
+    __syncthreads();
+    const int A = s_rec[0], S = s_rec[1], K = s_rec[2], flags = s_rec[3];
+    const int opw = OP_FIXED + A + S;
+    const int32_t* odims = s_rec + STEP_FIXED;
+    const int32_t* sdims = odims + A;
+    const int32_t* ops = sdims + S;
+    const uint32_t out_size = (uint32_t)s_rec[4];
+    const int sum_size = s_rec[6];
+    int32_t* s_otab = s_mem + ((rec_len + 3) & ~3);
+    int32_t* s_stab = s_otab + TO * K;
+    const uint32_t tile0 = (uint32_t)tile_x * (uint32_t)TO;
+    for (int t = threadIdx.x; t < TO; t += blockDim.x) {
+        uint32_t rem = tile0 + t;
+        int32_t off[MAXK];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) off[k] = 0;
+        if (rem < out_size) {
+            for (int a = A - 1; a >= 0; --a) {
+                const uint32_t d = (uint32_t)odims[a];
+                const uint32_t q = rem / d;
+                const int32_t digit = (int32_t)(rem - q * d);
+                rem = q;
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k)
+                    if (k < K) off[k] += digit * ops[k * opw + OP_FIXED + a];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+            if (k < K) s_otab[t * K + k] = off[k];
+    }
+    for (int qi = threadIdx.x; qi < sum_size; qi += blockDim.x) {
+        uint32_t rem = (uint32_t)qi;
+        int32_t off[MAXK];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) off[k] = 0;
+        for (int a = S - 1; a >= 0; --a) {
+            const uint32_t d = (uint32_t)sdims[a];
+            const uint32_t q = rem / d;
+            const int32_t digit = (int32_t)(rem - q * d);
+            rem = q;
+#pragma unroll
+            for (int k = 0; k < MAXK; ++k)
+                if (k < K) off[k] += digit * ops[k * opw + OP_FIXED + A + a];
+        }
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+            if (k < K) s_stab[qi * K + k] = off[k];
+    }
+    __syncthreads();
+
+    int n_mul = K;
+    if (flags & FLAG_DIV)
+        while (n_mul > 0 && (ops[(n_mul - 1) * opw] & 0x100)) --n_mul;
+    const bool use_max = (flags & FLAG_MAX) != 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint32_t out_base = ws_off0 + (uint32_t)s_rec[8] * ldb;
+    const int32_t* ev_card = pool + ev_card_off;
+    // operand classes (warp uniform): bit k of wsm = work table (vector load), bit k of evm = const with observed axes
+    int wsm = 0, evm = 0;
+    for (int k = 0; k < K; ++k) {
+        if ((ops[k * opw] & 0xFF) == 1) wsm |= 1 << k;
+        else if (ops[k * opw + 3] > 0) evm |= 1 << k;
+    }
+    for (int tb = 0; tb < btb; ++tb) {
+        const int64_t b = (((int64_t)b_block * btb + tb) * 32 + lane) * 2;  // this lane owns b and b + 1
+        if (b >= B) continue;                                             // no barriers below
+        const int64_t b1 = b + 1 < B ? b + 1 : b;                         // evidence row of the second set (clamped)
+        uint32_t rowb[MAXK], rowc[MAXK], unit[MAXK];  // rowc: second evidence set's base for const operands
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) {
+            rowb[k] = 0;
+            rowc[k] = 0;
+            unit[k] = 0;
+            if (k < K) {
+                const int32_t* op = ops + k * opw;
+                uint32_t e = (uint32_t)op[1], e1 = e;
+                const int ne = op[3];
+                if (ne > 0) {
+                    const int32_t* pairs = s_rec + op[4];
+                    for (int j = 0; j < ne; ++j) {
+                        const int slot = pairs[2 * j];
+                        const int32_t card = ev_card[slot];
+                        int32_t st = ev[b * n_ev + slot];
+                        st = st < 0 ? 0 : (st >= card ? card - 1 : st);
+                        e += (uint32_t)(st * pairs[2 * j + 1]);
+                        int32_t s1 = ev[b1 * n_ev + slot];
+                        s1 = s1 < 0 ? 0 : (s1 >= card ? card - 1 : s1);
+                        e1 += (uint32_t)(s1 * pairs[2 * j + 1]);
+                    }
+                }
+                if ((op[0] & 0xFF) == 1) {
+                    unit[k] = ldb;
+                    rowb[k] = ws_off0 + e * ldb + (uint32_t)b;
+                } else {
+                    unit[k] = 1;
+                    rowb[k] = e;
+                    rowc[k] = e1;
+                }
+            }
+        }
+        const uint32_t outb = out_base + (uint32_t)b;
+        for (int og = warp; og < TO; og += n_warps) {
+            const uint32_t o = tile0 + og;
+            if (o >= out_size) break;
+            const int32_t* ot = s_otab + og * K;
+            uint32_t p[MAXK];
+#pragma unroll
+            for (int k = 0; k < MAXK; ++k) p[k] = (k < K) ? (uint32_t)ot[k] * unit[k] : 0;
+            T a0, a1;
+            auto load = [&](int k, uint32_t off, T& x0, T& x1) {
+                if ((wsm >> k) & 1) {
+                    const V v = *reinterpret_cast<const V*>(ws_in + rowb[k] + off);
+                    x0 = v.x;
+                    x1 = v.y;
+                } else {
+                    x0 = ws_in[rowb[k] + off];
+                    x1 = ((evm >> k) & 1) ? ws_in[rowc[k] + off] : x0;
+                }
+            };
+            if (S == 0) {
+                T p0 = (T)1, p1 = (T)1;
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k) {
+                    if (k < n_mul) {
+                        T x0, x1;
+                        load(k, p[k], x0, x1);
+                        p0 *= x0;
+                        p1 *= x1;
+                    }
+                }
+                a0 = p0;
+                a1 = p1;
+            } else {
+                a0 = use_max ? neg_inf<T>() : (T)0;
+                a1 = a0;
+                const int32_t* st = s_stab;
+#pragma unroll 2
+                for (int q = 0; q < sum_size; ++q, st += K) {
+                    T p0 = (T)1, p1 = (T)1;
+#pragma unroll
+                    for (int k = 0; k < MAXK; ++k) {
+                        if (k < n_mul) {
+                            T x0, x1;
+                            load(k, p[k] + (uint32_t)st[k] * unit[k], x0, x1);
+                            p0 *= x0;
+                            p1 *= x1;
+                        }
+                    }
+                    if (use_max) {
+                        a0 = p0 > a0 ? p0 : a0;
+                        a1 = p1 > a1 ? p1 : a1;
+                    } else {
+                        a0 += p0;
+                        a1 += p1;
+                    }
+                }
+            }
+            if (flags & FLAG_DIV) {
+                T d0 = (T)1, d1 = (T)1;
+#pragma unroll
+                for (int k = 0; k < MAXK; ++k) {
+                    if (k >= n_mul && k < K) {
+                        T x0, x1;
+                        load(k, p[k], x0, x1);
+                        d0 *= x0;
+                        d1 *= x1;
+                    }
+                }
+                const T r0 = a0 / d0, r1 = a1 / d1;
+                a0 = (r0 != r0) ? (T)0 : r0;
+                a1 = (r1 != r1) ? (T)0 : r1;
+            }
+            V res;
+            res.x = a0;
+            res.y = a1;
+            *reinterpret_cast<V*>(ws_out + outb + o * ldb) = res;
+        }
+    }
+}
+
 // K3 — GEMM-shaped steps (two or three operands sharing the summed variables, each depending on only part of the
 // output scope; diabetes, parts of pathfinder/munin). Same launch contract and phase 1 as k_contract_tile32; in phase 2
 // a thread owns an R2 x R1 block of the output seen as a matrix [slower axes][fastest axis] and keeps R2*R1
@@ -971,6 +1184,7 @@ struct LaunchGroup {
 struct StepSchedule {
     int64_t B = 0;
     int step_kernel = 0, dtype_size = 0;
+    bool vec2 = false;  // tile groups use the two-evidence-sets-per-lane kernel (64 evidence sets per warp)
     std::vector<LaunchGroup> groups;
     TileItem* d_items = nullptr;
 };
@@ -1008,6 +1222,7 @@ struct pgx_plan {
     std::vector<StepSchedule> schedules;
     cudaStream_t cap_stream = nullptr;
     int last_graph = 0;
+    int vec2 = 1;         // tile kernel with two evidence sets per lane when B >= 64 (PGX_OPT_VEC2)
     int gemm_tile = 0;    // route GEMM-shaped steps to k_contract_gemm32 (PGX_OPT_GEMM_TILE); measured slower, opt-in
     int reg_tile = 0;     // register-tile GEMM-shaped steps (PGX_OPT_REG_TILE); measured neutral-to-slower, off by default
     int batch_levels = 1; // share one launch among the tile-eligible steps of a dependency level
@@ -1210,9 +1425,12 @@ int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
         case PGX_OPT_USE_GRAPH:
             plan->use_graph = value ? 1 : 0;
             return PGX_OK;
+        case PGX_OPT_VEC2:
         case PGX_OPT_GEMM_TILE:
         case PGX_OPT_REG_TILE:
-            if (option == PGX_OPT_GEMM_TILE) plan->gemm_tile = value ? 1 : 0; else plan->reg_tile = value ? 1 : 0;
+            if (option == PGX_OPT_GEMM_TILE) plan->gemm_tile = value ? 1 : 0;
+            else if (option == PGX_OPT_VEC2) plan->vec2 = value ? 1 : 0;
+            else plan->reg_tile = value ? 1 : 0;
             for (StepSchedule& c : plan->schedules)
                 if (c.d_items) cudaFree(c.d_items);
             plan->schedules.clear();
@@ -1342,11 +1560,17 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
         // launch schedule for this batch size: tile-eligible steps of one dependency level share a launch
         StepSchedule* sched = nullptr;
         for (StepSchedule& c : pl->schedules)
-            if (c.B == B && c.step_kernel == pl->step_kernel + 4 * pl->batch_levels + 8 * pl->gemm_tile && c.dtype_size == (int)sizeof(T)) sched = &c;
+            if (c.B == B && c.step_kernel == pl->step_kernel + 4 * pl->batch_levels + 8 * pl->gemm_tile + 16 * pl->vec2 &&
+                c.dtype_size == (int)sizeof(T))
+                sched = &c;
         if (!sched) {
             StepSchedule ns;
             ns.B = B;
-            ns.step_kernel = pl->step_kernel + 4 * pl->batch_levels + 8 * pl->gemm_tile;
+            ns.step_kernel = pl->step_kernel + 4 * pl->batch_levels + 8 * pl->gemm_tile + 16 * pl->vec2;
+            // 16-byte lanes when the batch is wide enough and 32-bit addressing applies (checked again at launch)
+            ns.vec2 = pl->vec2 && pl->step_kernel == 0 && bt_log2 == 5 && B >= 64 && !pl->gemm_tile && !pl->reg_tile &&
+                      ws_off0 + (size_t)pl->ws_entries * (size_t)ldb < (1ULL << 32) && pl->ws_entries < (1LL << 31);
+            const int64_t tile_b_tiles = ns.vec2 ? (B + 63) / 64 : b_tiles;
             ns.dtype_size = (int)sizeof(T);
             std::vector<TileItem> items;
             const int o_per_warp = 32 >> bt_log2;
@@ -1390,13 +1614,13 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                     ns.groups.push_back(g);
                     continue;
                 }
-                int btb = (int)(b_tiles < 4 ? b_tiles : 4);
-                int64_t b_blocks = (b_tiles + btb - 1) / btb;
+                int btb = (int)(tile_b_tiles < 4 ? tile_b_tiles : (ns.vec2 ? 2 : 4));
+                int64_t b_blocks = (tile_b_tiles + btb - 1) / btb;
                 int64_t TO = (s.out_size * b_blocks) / (148 * 4);  // aim at >= 4 CTAs per SM when there is work
                 if (TO < 8 * o_per_warp) {
                     // little work along the output: one evidence tile per CTA, one entry per warp
                     btb = 1;
-                    b_blocks = b_tiles;
+                    b_blocks = tile_b_tiles;
                     TO = 8 * o_per_warp;
                 }
                 if (TO > 512) TO = 512;
@@ -1469,7 +1693,19 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
     k_contract_tile<T, MK, RT><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off, cst, \
                                                                           ws, ws, ev, pl->n_ev, B, ldb, bt_log2)
                     const bool rt = g.rtile && pl->reg_tile && bt_log2 == 5;
-                    if (idx32 && g.gemm) {
+                    if (idx32 && sched->vec2) {
+#define PGX_LAUNCH_TILE32V(MK)                                                                                              \
+    k_contract_tile32v<T, MK><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off, ws_all, \
+                                                                         ws_all, (uint32_t)ws_off0, ev, pl->n_ev, B,          \
+                                                                         (uint32_t)ldb)
+                        if (g.max_k <= 2)
+                            PGX_LAUNCH_TILE32V(2);
+                        else if (g.max_k <= 4)
+                            PGX_LAUNCH_TILE32V(4);
+                        else
+                            PGX_LAUNCH_TILE32V(8);
+#undef PGX_LAUNCH_TILE32V
+                    } else if (idx32 && g.gemm) {
                         if (g.max_k <= 2)
                             k_contract_gemm32<T, 2><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(
                                 pl->d_pool, d_it, g.n_items, pl->ev_card_off, ws_all, ws_all, (uint32_t)ws_off0, ev, pl->n_ev, B,

@@ -93,6 +93,9 @@ class CompiledPlan:
         v = self.info(N.INFO_LAST_VARIANT)
         return {0: "stepwise", 1: "generic", 2: "tables-smem", 3: "tables-global"}[v]
 
+    def set_vec2(self, enabled: bool = True):
+        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_VEC2, 1 if enabled else 0))
+
     def set_gemm_tile(self, enabled: bool = True):
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_GEMM_TILE, 1 if enabled else 0))
 

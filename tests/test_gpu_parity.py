@@ -648,3 +648,24 @@ def test_gemm_shaped_step_kernel_matches(torch_cuda, name):
     assert float(((tiled - plain).abs() / plain.abs().clamp_min(1e-300)).max()) <= 1e-13
     want = run_plan(plan.pool, plan.const_blob, states[:3])
     assert rel_err(tiled[:3].cpu().numpy(), want) <= 1e-12
+
+
+@pytest.mark.parametrize("name,B", [("hepar2", 64), ("hepar2", 333), ("pathfinder", 97), ("diabetes", 70)])
+def test_two_sets_per_lane_tile_kernel_matches(torch_cuda, name, B):
+    """k_contract_tile32v (16-byte lanes: evidence sets b and b+1 per lane) vs the scalar-lane kernel and the oracle,
+    including odd batch sizes where the last lane's second set is padding."""
+    torch = torch_cuda
+    m = px.get_example_model(name)
+    ev_vars, states = sample_evidence(m, B, 8, seed=17)
+    for distribute in ("auto", "divide"):
+        plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, distribute=distribute)
+        cp = _engine()(plan)
+        cp.set_mode("stepwise")
+        ev = torch.from_numpy(states).cuda()
+        cp.set_vec2(False)
+        scalar = cp.run(ev).clone()
+        cp.set_vec2(True)
+        vec = cp.run(ev)
+        assert torch.equal(vec, scalar)
+        want = run_plan(plan.pool, plan.const_blob, states[-3:])
+        assert rel_err(vec[-3:].cpu().numpy(), want) <= 1e-12

@@ -13,10 +13,12 @@ jt = JTStructure.from_model(m)
 ev_vars, states = sample_evidence(m, B, 8, seed=1)
 ev = torch.from_numpy(states).cuda()
 for d in sys.argv[3:] or ["ss", "belief", "divide"]:
-    gemm = not d.endswith("-nogemm")
-    plan = compile_jt_plan(jt, ev_vars, distribute=d.replace("-nogemm", ""))
+    gemm = d.endswith("-gemm")
+    vec2 = not d.endswith("-novec")
+    plan = compile_jt_plan(jt, ev_vars, distribute=d.replace("-gemm", "").replace("-novec", ""))
     cp = CompiledPlan(plan)
     cp.set_gemm_tile(gemm)
+    cp.set_vec2(vec2)
     out = torch.empty((B, cp.out_elems), dtype=torch.float64, device="cuda")
     for _ in range(2):
         cp.run(ev, out=out)
