@@ -70,7 +70,7 @@ extern "C" {
 
 #define PGX_OPT_GEMM_TILE 7    /* stepwise mode: 2-D register-tiled kernel for GEMM-shaped steps (default 0: measured slower) */
 
-#define PGX_OPT_VEC2 8         /* stepwise mode: two evidence sets per lane (16-byte loads) when B >= 64 (default 1) */
+#define PGX_OPT_VEC2 8         /* stepwise mode: two evidence sets per lane (16-byte loads) when B >= 64 (default 0) */
 
 #define PGX_INFO_N_STEPS 1
 #define PGX_INFO_OUT_ELEMS 2

@@ -1222,7 +1222,7 @@ struct pgx_plan {
     std::vector<StepSchedule> schedules;
     cudaStream_t cap_stream = nullptr;
     int last_graph = 0;
-    int vec2 = 1;         // tile kernel with two evidence sets per lane when B >= 64 (PGX_OPT_VEC2)
+    int vec2 = 0;         // tile kernel with two evidence sets per lane when B >= 64 (PGX_OPT_VEC2); measured slower, opt-in
     int gemm_tile = 0;    // route GEMM-shaped steps to k_contract_gemm32 (PGX_OPT_GEMM_TILE); measured slower, opt-in
     int reg_tile = 0;     // register-tile GEMM-shaped steps (PGX_OPT_REG_TILE); measured neutral-to-slower, off by default
     int batch_levels = 1; // share one launch among the tile-eligible steps of a dependency level
