@@ -203,6 +203,10 @@ inline bool build_micro(const int32_t* pool, std::vector<int32_t>& w, MicroInfo&
 
 #if defined(__CUDACC__)
 
+#ifndef PGX_FUSED_FAST_MINB
+#define PGX_FUSED_FAST_MINB 2  // 512-thread CTAs per SM the fast-only fused kernel is compiled for (64 registers)
+#endif
+
 // Fast path: plain sum-product step whose NC batch-invariant operands come first. Everything about the operand
 // list is a compile-time constant, so the inner loop is: offset-table load, add, value load, multiply.
 //   wsb   : work-table base for this lane (shared: ws_s + lane, global: ws_g + b)
@@ -326,7 +330,7 @@ __device__ __forceinline__ void micro_chunk(const int32_t* __restrict__ mp, cons
 // FAST_ONLY: every step of the plan has a fast code (plain sum-product, const operands first, <= 5 operands), so the
 // general chunk function is not compiled in — fewer registers, two 512-thread CTAs per SM.
 template <typename T, bool SMEM, bool FAST_ONLY>
-__global__ void __launch_bounds__(512, FAST_ONLY ? 2 : 1) k_plan_fused2(const int32_t* __restrict__ mp, const T* __restrict__ cst,
+__global__ void __launch_bounds__(512, FAST_ONLY ? PGX_FUSED_FAST_MINB : 1) k_plan_fused2(const int32_t* __restrict__ mp, const T* __restrict__ cst,
                                                      T* __restrict__ ws_g, const int32_t* __restrict__ ev,
                                                      const int32_t* __restrict__ ev_card, T* __restrict__ out, int n_ev,
                                                      int ws_entries, int64_t B, int64_t ldb) {
