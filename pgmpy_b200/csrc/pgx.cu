@@ -1512,16 +1512,9 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
         }
         if (G < 1) G = 1;
         if (G > 16) G = 16;
-        // persistent grid: a multiple of the SM count (as many CTAs as can be resident), never more than there are rows
-        int64_t grid_rows = rows;
-        if (smem) {
-            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (dyn + 1024)));
-            const int by_threads = std::max(1, (pl->micro.all_fast ? 1024 : 640) / (32 * G));
-            grid_rows = std::min<int64_t>(rows, 148LL * std::min(per_sm, by_threads));
-        }
 #define PGX_LAUNCH_FUSED2(SM, FO)                                                                                     \
-    k_plan_fused2<T, SM, FO><<<(unsigned)grid_rows, 32 * G, dyn, st>>>(pl->d_micro, cst, ws, ev, pl->d_pool + pl->ev_card_off, out, \
-                                                                       pl->n_ev, (int)pl->ws_entries, B, ldb)
+    k_plan_fused2<T, SM, FO><<<(unsigned)rows, 32 * G, dyn, st>>>(pl->d_micro, cst, ws, ev, pl->d_pool + pl->ev_card_off, out, \
+                                                                  pl->n_ev, (int)pl->ws_entries, B, ldb)
         if (smem && pl->micro.all_fast) {
             PGX_CUDA(cudaFuncSetAttribute(k_plan_fused2<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             PGX_LAUNCH_FUSED2(true, true);

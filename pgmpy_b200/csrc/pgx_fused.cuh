@@ -340,10 +340,7 @@ __global__ void __launch_bounds__(512, FAST_ONLY ? PGX_FUSED_FAST_MINB : 1) k_pl
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int G = blockDim.x >> 5;
-    // persistent CTAs: the grid is a multiple of the SM count and every CTA walks rows of 32 evidence sets
-    const int64_t n_rows = (B + FUSED_LANES - 1) / FUSED_LANES;
-    for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
-    const int64_t row0 = row * FUSED_LANES;
+    const int64_t row0 = (int64_t)blockIdx.x * FUSED_LANES;
     const int64_t b = row0 + lane;
     // evidence rows of this CTA -> shared [slot][lane], clamped into range
     for (int i = threadIdx.x; i < FUSED_LANES * n_ev; i += blockDim.x) {
@@ -430,8 +427,6 @@ __global__ void __launch_bounds__(512, FAST_ONLY ? PGX_FUSED_FAST_MINB : 1) k_pl
                 for (int i = 0; i < n; ++i) dst[i] = src[(int64_t)i * ldb];
             }
         }
-    }
-    __syncthreads();  // the next row reuses the shared work tables and evidence
     }
 }
 
