@@ -26,7 +26,9 @@
  * Conventions: plain pointers and sizes only; 0 = success, negative = error (pgx_last_error() gives the
  * text, thread local); no exceptions cross the boundary. The CALLER owns every device buffer
  * (table blob, evidence, output, workspace); a plan owns only device copies of its descriptors.
- * A plan may be run concurrently on different streams with different workspaces.
+ * A plan may be enqueued on several streams with different workspaces (the end-to-end ring of pgmpy_b200.engine does
+ * that); calls on the SAME plan from several host threads must be serialised by the caller (launch schedules and CUDA
+ * graphs are cached inside the plan).
  */
 #ifndef PGX_H
 #define PGX_H
