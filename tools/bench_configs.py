@@ -68,6 +68,31 @@ def alarm_ve(batch=1024):
                       "alg_GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / PEAK}), flush=True)
 
 
+def single_query_latency(name="alarm", n=200):
+    """Drop-in API latency: VariableElimination.query / BeliefPropagation.query for ONE evidence set (plan cached),
+    wall clock per call including H2D of the evidence, the launch sequence, D2H and DiscreteFactor construction.
+    The reference needs ~5.4 ms per alarm VE query on a CPU core (BASELINE.md probe)."""
+    m = px.get_example_model(name)
+    ve, bp = VariableElimination(m), BeliefPropagation(m)
+    ev_vars, states = sample_evidence(m, n, 5 if name == "alarm" else 8, seed=3)
+    free = [v for v in m.nodes() if v not in ev_vars]
+    rows = [{v: m.states[v][int(s)] for v, s in zip(ev_vars, st)} for st in states]
+    res = {}
+    for label, infer in (("ve", ve), ("bp", bp)):
+        infer.query([free[0]], evidence=rows[0])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(n):
+            infer.query([free[0]], evidence=rows[i])
+        res[label] = (time.perf_counter() - t0) / n * 1e6
+        # a new query variable = a new plan: compile + upload + first run
+        t0 = time.perf_counter()
+        infer.query([free[1]], evidence=rows[0])
+        res[label + "_cold_ms"] = (time.perf_counter() - t0) * 1e3
+    print(json.dumps({"config": f"{name} single-query latency through the drop-in API", "ve_query_us": res["ve"],
+                      "bp_query_us": res["bp"], "ve_new_signature_ms": res["ve_cold_ms"], "bp_new_signature_ms": res["bp_cold_ms"]}), flush=True)
+
+
 def mixed_ve(name, batch=262144, n_sig=16):
     """configs[2]: hepar2 / win95pts VE (min-fill order), mixed evidence: 16 observed sets per batch, equal shares."""
     m = px.get_example_model(name)
@@ -119,6 +144,9 @@ def bp_all_marginals(name, batch, k=8, reps=3, reg_tile=False):
 
 if __name__ == "__main__":
     what = sys.argv[1:] or ["alarm_ve", "mixed_ve", "large", "munin"]
+    if "latency" in what:
+        single_query_latency("alarm")
+        single_query_latency("hepar2")
     if "alarm_ve" in what:
         alarm_ve()
     if "mixed_ve" in what:
