@@ -699,3 +699,21 @@ def test_engine_argument_errors(torch_cuda):
     assert torch.isfinite(cp.run(ev_bad)[1:]).all()
     with pytest.raises(PgxError):
         cp.set_mode("fused", 99)
+
+
+@pytest.mark.parametrize("name", ["alarm", "child"])
+def test_map_query_and_max_marginal_vs_reference_golden(torch_cuda, name):
+    """map_query / max_marginal against values produced by the unmodified reference (oracle/make_golden_map.py)."""
+    import json
+    import os
+
+    from pgmpy_b200.inference import VariableElimination
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", f"ref_{name}_map.json")) as f:
+        g = json.load(f)
+    m = px.get_example_model(name)
+    ve = VariableElimination(m)
+    for c in g["cases"]:
+        ev = {v: m.states[v][int(s)] for v, s in zip(g["ev_vars"], g["ev_states"][c["case"]])}
+        assert ve.map_query(c["variables"], evidence=ev) == c["map"]
+        assert abs(ve.max_marginal(c["variables"], evidence=ev) - c["max_marginal"]) <= 1e-12 * c["max_marginal"]
