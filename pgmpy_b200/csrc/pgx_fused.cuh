@@ -16,7 +16,6 @@
 //   levels[n_levels+1]: first item of each level
 //   items[n_items][3]:  (step record offset, first output entry, number of consecutive entries)  — a chunk of a step
 //   step record: 0 K | 1 n_mul | 2 flags | 3 sum_size | 4 out_off | 5 otab_off | 6 stab_off | 7 wsmask | 8 evmask | 9 fast code
-//                | 10 ptab_off (packed table: one 64-bit word = four 16-bit entry offsets per (o, s), or -1)
 //                (fast code = K*8 + #leading const operands when the step is a plain sum-product whose const operands
 //                 come first, else -1: selects a fully specialised instantiation of the chunk function)
 //                | then per operand (n_ev, ev_pairs_off) ; otab[out_size][K] ; stab[sum_size][K] ; ev pairs (slot, stride)
@@ -30,7 +29,7 @@
 namespace pgx {
 
 constexpr int MW_HEADER = 8;
-constexpr int SR_FIXED = 11;
+constexpr int SR_FIXED = 10;
 constexpr int ITEM_WORDS = 3;
 constexpr int FUSED_LANES = 32;
 
@@ -145,32 +144,6 @@ inline bool build_micro(const int32_t* pool, std::vector<int32_t>& w, MicroInfo&
                 sd[a] = 0;
             }
         }
-        // packed per-(o, s) table for the fast path: all K (<= 4) entry offsets of one product in one 64-bit load
-        w[srec + 10] = -1;
-        if (w[srec + 9] >= 0 && K <= 4 && out_size * sum_size <= (1 << 16) &&
-            (int64_t)w.size() + 2 * out_size * sum_size + 2 <= max_words) {
-            bool fits = true;
-            for (int k = 0; k < K && fits; ++k) {
-                const int32_t* op = ops + k * opw;
-                int64_t hi = ld_i64(op + 1);
-                for (int a = 0; a < A; ++a) hi += (int64_t)(odims[a] - 1) * op[OP_FIXED + a];
-                for (int a = 0; a < S; ++a) hi += (int64_t)(sdims[a] - 1) * op[OP_FIXED + A + a];
-                if (hi > 0xFFFF) fits = false;  // evidence offsets are added in registers, not packed
-            }
-            if (fits) {
-                if (w.size() & 1) w.push_back(0);  // 8-byte alignment of the 64-bit words
-                const int ptab = (int)w.size();
-                w[srec + 10] = ptab;
-                w.resize(w.size() + 2 * (size_t)(out_size * sum_size), 0);
-                for (int64_t o = 0; o < out_size; ++o)
-                    for (int64_t q = 0; q < sum_size; ++q) {
-                        uint32_t e[4] = {0, 0, 0, 0};
-                        for (int k = 0; k < K; ++k) e[k] = (uint32_t)(w[otab + o * K + k] + w[stab + q * K + k]);
-                        w[ptab + 2 * (o * sum_size + q)] = (int32_t)(e[0] | (e[1] << 16));
-                        w[ptab + 2 * (o * sum_size + q) + 1] = (int32_t)(e[2] | (e[3] << 16));
-                    }
-            }
-        }
         for (int k = 0; k < K; ++k) {
             const int32_t* op = ops + k * opw;
             const int n_ev = op[3];
@@ -271,49 +244,6 @@ __device__ __forceinline__ void micro_chunk_fast(const int32_t* __restrict__ mp,
             for (int k = 0; k < K; ++k) {
                 const int32_t off = boff[k] + __ldg(st + k);
                 const T v = (k < NC) ? __ldg(cst + off) : (SMEM ? wsb[off * FUSED_LANES] : wsb[(int64_t)off * pitch]);
-                prod = (k == 0) ? v : prod * v;
-            }
-            acc += prod;
-        }
-        if (SMEM)
-            wsb[(out_off + o) * FUSED_LANES] = acc;
-        else
-            wsb[(int64_t)(out_off + o) * pitch] = acc;
-    }
-}
-
-// Fast path with the packed table: one 64-bit load yields the K (<= 4) entry offsets of a product, so the inner loop
-// is: table load, K x (extract, address, value load, multiply). No otab/stab adds, no per-entry table row.
-template <typename T, int K, int NC, bool SMEM>
-__device__ __forceinline__ void micro_chunk_packed(const int32_t* __restrict__ mp, const int32_t* __restrict__ sr, int o0,
-                                                   int n_o, const T* __restrict__ cst, T* wsb, int64_t pitch,
-                                                   const int32_t* __restrict__ evs, int lane) {
-    const int sum_size = __ldg(sr + 3);
-    const int out_off = __ldg(sr + 4);
-    const int evmask = __ldg(sr + 8);
-    const uint2* pt = reinterpret_cast<const uint2*>(mp + __ldg(sr + 10)) + (int64_t)o0 * sum_size;
-    int32_t evo[NC > 0 ? NC : 1];
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        evo[k] = 0;
-        if ((evmask >> k) & 1) {
-            const int n_ev = __ldg(sr + SR_FIXED + 2 * k);
-            const int32_t* pairs = mp + __ldg(sr + SR_FIXED + 2 * k + 1);
-            for (int j = 0; j < n_ev; ++j) evo[k] += evs[__ldg(pairs + 2 * j) * FUSED_LANES + lane] * __ldg(pairs + 2 * j + 1);
-        }
-    }
-    for (int o = o0; o < o0 + n_o; ++o) {
-        T acc = (T)0;
-#pragma unroll 2
-        for (int s = 0; s < sum_size; ++s, ++pt) {
-            const uint2 wd = __ldg(pt);
-            T prod;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const uint32_t half = (k < 2) ? wd.x : wd.y;
-                const int32_t off = (int32_t)((k & 1) ? (half >> 16) : (half & 0xFFFFu));
-                const T v = (k < NC) ? __ldg(cst + off + evo[k < NC ? k : 0])
-                                     : (SMEM ? wsb[off * FUSED_LANES] : wsb[(int64_t)off * pitch]);
                 prod = (k == 0) ? v : prod * v;
             }
             acc += prod;
@@ -435,13 +365,8 @@ __global__ void __launch_bounds__(512, FAST_ONLY ? PGX_FUSED_FAST_MINB : 1) k_pl
             const int o0 = __ldg(items + ITEM_WORDS * i + 1);
             const int n_o = __ldg(items + ITEM_WORDS * i + 2);
             if (SMEM || b < B) {
-#define PGX_FAST(KK, NN)                                                                       \
-    case KK * 8 + NN:                                                                          \
-        if (KK <= 4 && __ldg(sr + 10) >= 0)                                                    \
-            micro_chunk_packed<T, (KK <= 4 ? KK : 4), (NN <= 4 ? NN : 4), SMEM>(mp, sr, o0, n_o, cst, wsb, ldb, evs, lane); \
-        else                                                                                   \
-            micro_chunk_fast<T, KK, NN, SMEM>(mp, sr, o0, n_o, cst, wsb, ldb, evs, lane);      \
-        break;
+#define PGX_FAST(KK, NN) \
+    case KK * 8 + NN: micro_chunk_fast<T, KK, NN, SMEM>(mp, sr, o0, n_o, cst, wsb, ldb, evs, lane); break;
                 switch (__ldg(sr + 9)) {
                     PGX_FAST(1, 0) PGX_FAST(1, 1)
                     PGX_FAST(2, 0) PGX_FAST(2, 1) PGX_FAST(2, 2)
