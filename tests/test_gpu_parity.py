@@ -717,3 +717,18 @@ def test_map_query_and_max_marginal_vs_reference_golden(torch_cuda, name):
         ev = {v: m.states[v][int(s)] for v, s in zip(g["ev_vars"], g["ev_states"][c["case"]])}
         assert ve.map_query(c["variables"], evidence=ev) == c["map"]
         assert abs(ve.max_marginal(c["variables"], evidence=ev) - c["max_marginal"]) <= 1e-12 * c["max_marginal"]
+
+
+def test_wide_operand_steps_without_reassociation(torch_cuda, monkeypatch):
+    """With the greedy re-association off, hepar2's 17-neighbour clique yields steps of up to 16 operands: the
+    MAX_OPS-wide instantiations of every kernel (generic step kernel, generic fused chunk, first-generation fused)."""
+    monkeypatch.setenv("PGX_NO_REASSOC", "1")
+    m = px.get_example_model("hepar2")
+    ev_vars, states = sample_evidence(m, 40, 8, seed=23)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, distribute="ss")
+    assert max(len(st.operands) for st in plan.steps) > 8
+    want = run_plan(plan.pool, plan.const_blob, states)
+    for mode, kernel, step_kernel in EXEC_VARIANTS:
+        cp = _engine()(plan)
+        cp.set_mode(mode, 0, kernel, step_kernel)
+        assert rel_err(cp.run_host(states), want) <= 1e-12
