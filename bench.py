@@ -268,6 +268,8 @@ def run_b200(args):
     numa_cpus = bind_process_to_gpu_numa(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     cfg, k = workload_config(args, n_gpus)
