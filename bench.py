@@ -268,8 +268,7 @@ def run_b200(args):
     numa_cpus = bind_process_to_gpu_numa(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner/log lines go to stderr: stdout = one JSON line
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     cfg, k = workload_config(args, n_gpus)
