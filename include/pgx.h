@@ -117,6 +117,13 @@ int pgx_run_batch(pgx_plan* plan, const int32_t* ev_states, void* out, void* wor
 int pgx_profile_steps(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
                       int64_t B, void* stream, float* step_ms, int32_t n_steps);
 
+/* Tracing aid: the same pass with the production launch schedule (steps of one dependency level share a launch).
+ * launch_ms[i] = device time of launch i (cap_launches >= number of launches), step_launch[s] = launch that served
+ * plan step s (n_steps >= the plan's step count), *n_launches = launches recorded. Synchronises the stream. */
+int pgx_profile_launches(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
+                         int64_t B, void* stream, float* launch_ms, int32_t cap_launches, int32_t* step_launch,
+                         int32_t n_steps, int32_t* n_launches);
+
 int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value);
 int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value);
 

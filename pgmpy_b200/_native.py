@@ -20,6 +20,7 @@ EXPORTS = (
     "pgx_workspace_bytes",
     "pgx_run_batch",
     "pgx_profile_steps",
+    "pgx_profile_launches",
     "pgx_plan_set_option",
     "pgx_plan_get_info",
     "pgx_evidence_reduce",
@@ -75,6 +76,11 @@ def load():
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p, C.POINTER(C.c_float), C.c_int32,
     ]
     lib.pgx_profile_steps.restype = C.c_int
+    lib.pgx_profile_launches.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p, C.POINTER(C.c_float), C.c_int32,
+        i32p, C.c_int32, i32p,
+    ]
+    lib.pgx_profile_launches.restype = C.c_int
     lib.pgx_plan_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
     lib.pgx_plan_set_option.restype = C.c_int
     lib.pgx_plan_get_info.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]

@@ -8,7 +8,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpgx.so")
 SOURCES = [os.path.join(CSRC, "pgx.cu")]
-HEADERS = [os.path.join(CSRC, "pgx_step.cuh"), os.path.join(os.path.dirname(HERE), "include", "pgx.h")]
+
+
+def _headers():
+    """Every header the library is compiled from: a stale .so must never be benchmarked silently."""
+    import glob
+
+    return sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h"))) + [
+        os.path.join(os.path.dirname(HERE), "include", "pgx.h")]
+
 
 
 def nvcc_path():
@@ -22,7 +30,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
+    return any(os.path.getmtime(p) > t for p in SOURCES + _headers())
 
 
 def build_native(force=False, verbose=False):

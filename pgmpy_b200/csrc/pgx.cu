@@ -1179,6 +1179,7 @@ struct LaunchGroup {
     size_t smem = 0;
     bool rtile = false;  // the group holds GEMM-shaped steps: use the register-tiled instantiation
     bool gemm = false;   // every step of the group goes to k_contract_gemm32 (2-D register tile)
+    std::vector<int> step_ids;  // plan steps served by this launch (tracing: pgx_profile_launches)
 };
 
 struct StepSchedule {
@@ -1230,6 +1231,7 @@ struct pgx_plan {
     int step_kernel = 0;  // 0 = auto (tile-cooperative where possible), 1 = generic per-thread kernel only
     int fused_kernel = 0; // 0 = auto, 1 = generic (v1), 2 = table-driven/shared workspace, 3 = table-driven/global workspace
     int last_variant = 0;
+    int last_sched = -1;  // index into `schedules` of the most recent stepwise run
     // info
     int64_t last_launches = 0;
     int last_mode = 0;
@@ -1611,6 +1613,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                     LaunchGroup g;
                     g.generic_step = (int)si;
                     g.n_items = 1;
+                    g.step_ids.push_back((int)si);
                     ns.groups.push_back(g);
                     continue;
                 }
@@ -1638,6 +1641,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                 if (cg.n_items > 0 && (int64_t)cg.n_blocks + n_blocks > (1LL << 30)) flush(cg);
                 pending[gemm_ok ? 1 : 0].push_back(TileItem{s.rec_off, s.rec_len, (int32_t)TO, btb, (int32_t)b_blocks, (int32_t)cg.n_blocks});
                 cg.gemm = gemm_ok;
+                cg.step_ids.push_back((int)si);
                 cg.n_items += 1;
                 cg.n_blocks += (int)n_blocks;
                 cg.max_k = std::max(cg.max_k, s.n_ops);
@@ -1658,6 +1662,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
             pl->schedules.push_back(ns);
             sched = &pl->schedules.back();
         }
+        pl->last_sched = (int)(sched - pl->schedules.data());
         // 32-bit addressing needs every element index (table copy + work tables) below 2^32
         const bool idx32 = pl->step_kernel == 0 && ws_off0 + (size_t)pl->ws_entries * (size_t)ldb < (1ULL << 32) &&
                            pl->ws_entries < (1LL << 31);
@@ -1811,28 +1816,68 @@ int pgx_run_batch(pgx_plan* plan, const int32_t* ev_states, void* out, void* wor
     return run_typed<float>(plan, ev_states, out, workspace, B, st);
 }
 
+// Shared body of the two tracing entry points: a stepwise pass with one CUDA event per launch.
+static int profile_pass(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
+                        int64_t B, void* stream, bool per_step, std::vector<float>& ms) {
+    const int saved_mode = plan->mode, saved_batch = plan->batch_levels;
+    std::vector<cudaEvent_t> evs((size_t)plan->n_steps + 2, nullptr);
+    int rc = PGX_OK;
+    for (auto& e : evs)
+        if (cudaEventCreate(&e) != cudaSuccess) rc = fail(PGX_ERR_CUDA, "cudaEventCreate failed");
+    if (rc == PGX_OK) {
+        plan->mode = PGX_MODE_STEPWISE;
+        if (per_step) plan->batch_levels = 0;  // one launch per step so that every step gets its own event pair
+        plan->prof_events = evs.data();
+        if (cudaEventRecord(evs[0], (cudaStream_t)stream) != cudaSuccess) rc = fail(PGX_ERR_CUDA, "cudaEventRecord failed");
+        if (rc == PGX_OK) rc = pgx_run_batch(plan, ev_states, out, workspace, workspace_bytes, B, stream);
+        plan->prof_events = nullptr;
+        plan->mode = saved_mode;
+        plan->batch_levels = saved_batch;
+    }
+    if (rc == PGX_OK && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
+        rc = fail(PGX_ERR_CUDA, "cudaStreamSynchronize failed");
+    if (rc == PGX_OK) {
+        const size_t n = plan->last_sched >= 0 ? plan->schedules[plan->last_sched].groups.size() : 0;
+        ms.assign(n, 0.f);
+        for (size_t i = 0; i < n && i + 1 < evs.size(); ++i)
+            if (cudaEventElapsedTime(&ms[i], evs[i], evs[i + 1]) != cudaSuccess) rc = fail(PGX_ERR_CUDA, "cudaEventElapsedTime failed");
+    }
+    for (auto& e : evs)
+        if (e) cudaEventDestroy(e);
+    return rc;
+}
+
 int pgx_profile_steps(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
                       int64_t B, void* stream, float* step_ms, int32_t n_steps) {
     if (!plan || !step_ms) return fail(PGX_ERR_INVALID, "null argument");
     if (n_steps < plan->n_steps) return fail(PGX_ERR_INVALID, "step_ms too short");
-    const int saved_mode = plan->mode;
-    std::vector<cudaEvent_t> evs(plan->n_steps + 1);
-    for (auto& e : evs) PGX_CUDA(cudaEventCreate(&e));
-    plan->mode = PGX_MODE_STEPWISE;
-    const int saved_batch = plan->batch_levels;
-    plan->batch_levels = 0;  // one launch per step so that every step gets its own event pair
-    plan->prof_events = evs.data();
-    PGX_CUDA(cudaEventRecord(evs[0], (cudaStream_t)stream));
-    const int rc = pgx_run_batch(plan, ev_states, out, workspace, workspace_bytes, B, stream);
-    plan->prof_events = nullptr;
-    plan->mode = saved_mode;
-    plan->batch_levels = saved_batch;
-    if (rc == PGX_OK) {
-        PGX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-        for (int i = 0; i < plan->n_steps; ++i) PGX_CUDA(cudaEventElapsedTime(&step_ms[i], evs[i], evs[i + 1]));
+    std::vector<float> ms;
+    const int rc = profile_pass(plan, ev_states, out, workspace, workspace_bytes, B, stream, true, ms);
+    if (rc != PGX_OK) return rc;
+    // with one launch per step the launch groups are the steps, in plan order
+    const StepSchedule& sc = plan->schedules[plan->last_sched];
+    for (int i = 0; i < plan->n_steps; ++i) step_ms[i] = 0.f;
+    for (size_t g = 0; g < sc.groups.size(); ++g)
+        for (int si : sc.groups[g].step_ids) step_ms[si] += ms[g];
+    return PGX_OK;
+}
+
+int pgx_profile_launches(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
+                         int64_t B, void* stream, float* launch_ms, int32_t cap_launches, int32_t* step_launch,
+                         int32_t n_steps, int32_t* n_launches) {
+    if (!plan || !launch_ms || !step_launch || !n_launches) return fail(PGX_ERR_INVALID, "null argument");
+    if (n_steps < plan->n_steps) return fail(PGX_ERR_INVALID, "step_launch too short");
+    std::vector<float> ms;
+    const int rc = profile_pass(plan, ev_states, out, workspace, workspace_bytes, B, stream, false, ms);
+    if (rc != PGX_OK) return rc;
+    const StepSchedule& sc = plan->schedules[plan->last_sched];
+    if ((int64_t)sc.groups.size() > cap_launches) return fail(PGX_ERR_INVALID, "launch_ms too short");
+    *n_launches = (int32_t)sc.groups.size();
+    for (size_t g = 0; g < sc.groups.size(); ++g) {
+        launch_ms[g] = ms[g];
+        for (int si : sc.groups[g].step_ids) step_launch[si] = (int32_t)g;
     }
-    for (auto& e : evs) cudaEventDestroy(e);
-    return rc;
+    return PGX_OK;
 }
 
 int pgx_evidence_reduce(int32_t dtype, const void* table, int64_t table_entries, int32_t n_free,
@@ -1870,24 +1915,29 @@ int pgx_evidence_reduce(int32_t dtype, const void* table, int64_t table_entries,
         h[3 * MAX_AXES + j] = ev_strides[j];
         h[4 * MAX_AXES + j] = ev_cards[j];
     }
-    PGX_CUDA(cudaMallocAsync((void**)&d, sizeof(h), st));
-    PGX_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, st));
-    const int64_t bt = ldb < 32 ? ldb : 32;
-    const int bt_log2 = ilog2_floor(bt);
+    // the kernel tiles the batch by a power of two: derive the tile count from THAT width (ldb = 24 would otherwise
+    // launch one tile of 16 sets and leave rows 16.. unwritten)
+    const int bt_log2 = ilog2_floor(ldb < 32 ? ldb : 32);
+    const int64_t bt = 1LL << bt_log2;
     const int64_t b_tiles = (B + bt - 1) / bt;
     if (b_tiles > 65535) return fail(PGX_ERR_UNSUPPORTED, "batch too large");
-    const int per_block = 256 >> bt_log2;
-    dim3 grid((unsigned)((n + per_block - 1) / per_block), (unsigned)b_tiles);
-    if (dtype == PGX_F64)
-        k_evidence_gather<double><<<grid, 256, 0, st>>>((const double*)table, n_free, d, d + MAX_AXES, n_ev,
-                                                        d + 2 * MAX_AXES, d + 3 * MAX_AXES, d + 4 * MAX_AXES, ev_states,
-                                                        ev_row_len, (double*)dst, n, B, ldb, bt_log2);
-    else
-        k_evidence_gather<float><<<grid, 256, 0, st>>>((const float*)table, n_free, d, d + MAX_AXES, n_ev,
-                                                       d + 2 * MAX_AXES, d + 3 * MAX_AXES, d + 4 * MAX_AXES, ev_states,
-                                                       ev_row_len, (float*)dst, n, B, ldb, bt_log2);
-    PGX_CUDA(cudaGetLastError());
-    PGX_CUDA(cudaFreeAsync(d, st));
+    PGX_CUDA(cudaMallocAsync((void**)&d, sizeof(h), st));
+    cudaError_t ce = cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) {
+        const int per_block = 256 >> bt_log2;
+        dim3 grid((unsigned)((n + per_block - 1) / per_block), (unsigned)b_tiles);
+        if (dtype == PGX_F64)
+            k_evidence_gather<double><<<grid, 256, 0, st>>>((const double*)table, n_free, d, d + MAX_AXES, n_ev,
+                                                            d + 2 * MAX_AXES, d + 3 * MAX_AXES, d + 4 * MAX_AXES, ev_states,
+                                                            ev_row_len, (double*)dst, n, B, ldb, bt_log2);
+        else
+            k_evidence_gather<float><<<grid, 256, 0, st>>>((const float*)table, n_free, d, d + MAX_AXES, n_ev,
+                                                           d + 2 * MAX_AXES, d + 3 * MAX_AXES, d + 4 * MAX_AXES, ev_states,
+                                                           ev_row_len, (float*)dst, n, B, ldb, bt_log2);
+        ce = cudaGetLastError();
+    }
+    cudaFreeAsync(d, st);  // stream ordered: after the kernel on every path
+    if (ce != cudaSuccess) return fail(PGX_ERR_CUDA, std::string("pgx_evidence_reduce: ") + cudaGetErrorString(ce));
     return PGX_OK;
 }
 

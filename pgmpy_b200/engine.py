@@ -197,6 +197,33 @@ class CompiledPlan:
             rows.append((float(t), st.out.size, ssz, len(st.operands), item * (B * work + const), st.level))
         return rows
 
+    def profile_launches(self, ev_states):
+        """Device time of every launch of one stepwise pass with the production schedule (steps of a dependency level
+        share a launch). Returns a list of dicts: ms, steps (indices into plan.steps), alg_bytes."""
+        torch = _torch()
+        B = ev_states.shape[0]
+        out = torch.empty((B, self.out_elems), dtype=self.torch_dtype, device=self.device)
+        need = self.workspace_bytes(B)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        n = max(1, self.plan.n_steps)
+        ms = (C.c_float * n)()
+        owner = (C.c_int32 * n)()
+        n_l = C.c_int32(0)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        N.check(self.lib.pgx_profile_launches(self.handle, C.c_void_p(ev_states.data_ptr() if self.n_ev else 0),
+                                              C.c_void_p(out.data_ptr()), C.c_void_p(self._ws.data_ptr()), self._ws.numel(), B,
+                                              C.c_void_p(stream), ms, n, owner, n, C.byref(n_l)))
+        item = 8 if self.dtype_name == "float64" else 4
+        rows = [{"ms": float(ms[i]), "steps": [], "alg_bytes": 0} for i in range(n_l.value)]
+        for si, st in enumerate(self.plan.steps):
+            work = st.out.size + sum(tb.size for tb, _ in st.operands if tb.kind == 1)
+            const = sum(tb.size for tb, _ in st.operands if tb.kind == 0)
+            r = rows[owner[si]]
+            r["steps"].append(si)
+            r["alg_bytes"] += item * (B * work + const)
+        return rows
+
     def run_pinned(self, ev_pinned, out_pinned, n_chunks: int = 0, n_streams: int = 3):
         """End-to-end call with HOST buffers: pinned int32 [B, n_ev] in, pinned [B, out_elems] out.
 

@@ -12,7 +12,7 @@ from oracle.plan_exec import run_plan
 from pgmpy_b200.evidence import sample_evidence
 from pgmpy_b200.planner import JTStructure, compile_jt_plan, compile_ve_plan
 
-from helpers import (SIX_NODE_ANSWERS, SNOW_ANSWERS, SNOW_VIRTUAL_1, SNOW_VIRTUAL_2, bp_reference_tolerance,
+from helpers import (SIX_NODE_ANSWERS, SNOW_ANSWERS, SNOW_VIRTUAL_1, SNOW_VIRTUAL_2, BP_QUERY_REFERENCE_RESIDUAL, golden_bp_models, load_golden_bp,
                      golden_models, load_golden, rel_err, six_node_net, snow_net)
 
 pytestmark = pytest.mark.gpu
@@ -90,9 +90,48 @@ def test_ve_query_batch_vs_reference_golden(torch_cuda, name):
     assert worst <= 1e-12, worst
 
 
-@pytest.mark.parametrize("name", [n for n in golden_models() if n not in ("sachs", "munin", "diabetes")])
+@pytest.mark.parametrize("name", ["pathfinder", "munin", "diabetes"])
+def test_ve_query_batch_vs_reference_golden_protocol_sizes(torch_cuda, name):
+    """VE mode on the large models at the SURVEY 8d protocol sizes (64 / 16 / 16 evidence sets x 8 query variables)."""
+    from pgmpy_b200.inference import VariableElimination
+
+    g = load_golden_bp(name, "ve")
+    ve = VariableElimination(px.get_example_model(name))
+    by_q = {}
+    for case, q, want in g["items"]:
+        by_q.setdefault(q, []).append((case, want))
+    worst = 0.0
+    for q, items in by_q.items():
+        out = ve.query_batch([q], g["ev_vars"], g["ev_states"]).cpu().numpy()
+        for case, want in items:
+            worst = max(worst, rel_err(out[case], want))
+    assert worst <= 1e-12, worst
+
+
+@pytest.mark.parametrize("name", golden_bp_models())
 def test_bp_marginals_batch_vs_reference_golden(torch_cuda, name):
-    """BeliefPropagation.marginals_batch vs the unmodified reference's BeliefPropagation.query on our tree."""
+    """BeliefPropagation.marginals_batch vs BP-mode posteriors of the unmodified reference at a FIXED 1e-12: the
+    reference's exact classic VE over all factors (tests/golden/refbp_*, oracle/make_golden_bp.py) on 256 evidence sets
+    (alarm, hepar2, win95pts), 64 (pathfinder), 16 (munin, diabetes)."""
+    from pgmpy_b200.inference import BeliefPropagation
+
+    g = load_golden_bp(name)
+    m = px.get_example_model(name)
+    bp = BeliefPropagation(m)
+    cp = bp.marginals_plan(g["ev_vars"])
+    out = bp.marginals_batch(g["ev_vars"], g["ev_states"]).cpu().numpy()
+    col = {s.vars[0]: (s.out_offset, s.table.size) for s in cp.plan.segments}
+    worst = 0.0
+    for case, q, want in g["items"]:
+        o, n = col[q]
+        worst = max(worst, rel_err(out[case, o : o + n], want))
+    assert worst <= 1e-12, worst
+
+
+@pytest.mark.parametrize("name", [n for n in golden_models() if n not in ("sachs", "munin", "diabetes")])
+def test_bp_marginals_batch_vs_reference_bp_query(torch_cuda, name):
+    """Secondary check: the reference's own BeliefPropagation.query on our tree. Its output is only as exact as its
+    iterate-until-allclose calibration, so it is held to that stopping rule (fixed), and the residual is reported."""
     from pgmpy_b200.inference import BeliefPropagation
 
     g = load_golden(name)
@@ -101,15 +140,12 @@ def test_bp_marginals_batch_vs_reference_golden(torch_cuda, name):
     cp = bp.marginals_plan(g["ev_vars"])
     out = bp.marginals_batch(g["ev_vars"], g["ev_states"]).cpu().numpy()
     col = {s.vars[0]: (s.out_offset, s.table.size) for s in cp.plan.segments}
-    # extended-precision evaluation of the same closed form pins our result; the reference's BP output is
-    # only as exact as its allclose stopping rule (helpers.bp_reference_tolerance)
-    exact = run_plan(cp.plan.pool, cp.plan.const_blob, g["ev_states"], dtype=np.longdouble).astype(np.float64)
-    assert rel_err(out, exact) <= 1e-12
+    worst = 0.0
     for case, q, want in g["bp"]:
         o, n = col[q]
-        tol = bp_reference_tolerance(want, exact[case, o : o + n])
-        assert tol <= 1e-6
-        assert rel_err(out[case, o : o + n], want) <= tol, (q, tol)
+        worst = max(worst, rel_err(out[case, o : o + n], want))
+    print(f"{name}: max rel difference to the reference's BeliefPropagation.query = {worst:.2e}")
+    assert worst <= BP_QUERY_REFERENCE_RESIDUAL, worst
 
 
 @pytest.mark.parametrize("name", ["pathfinder", "munin", "diabetes"])

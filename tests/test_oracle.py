@@ -7,7 +7,7 @@ import pgmpy_b200 as px
 from oracle import pgm_oracle as O
 from pgmpy_b200.planner import JTStructure
 
-from helpers import (SIX_NODE_ANSWERS, SNOW_ANSWERS, bp_reference_tolerance, golden_models, load_golden, rel_err,
+from helpers import (SIX_NODE_ANSWERS, SNOW_ANSWERS, BP_QUERY_REFERENCE_RESIDUAL, golden_bp_models, load_golden_bp, golden_models, load_golden, rel_err,
                      six_node_net, snow_net)
 
 
@@ -73,24 +73,34 @@ def test_ve_mode_matches_reference_golden(name):
     assert worst <= 1e-12, worst
 
 
+@pytest.mark.parametrize("name", golden_bp_models())
+def test_bp_mode_closed_form_matches_reference_golden(name):
+    """Oracle BP mode (all factors, no pruning) vs the reference's exact classic VE over all factors, fixed 1e-12."""
+    g = load_golden_bp(name)
+    m = px.get_example_model(name)
+    net = O.Net(m)
+    limit = {"munin": 6, "diabetes": 3, "pathfinder": 16}.get(name, 64)
+    worst = 0.0
+    for case, q, want in g["items"][:limit]:
+        ev = {v: m.states[v][int(s)] for v, s in zip(g["ev_vars"], g["ev_states"][case])}
+        got = O.ve_query(net, [q], ev, prune_model=False)
+        worst = max(worst, rel_err(got.values, want))
+    assert worst <= 1e-12, worst
+
+
 @pytest.mark.parametrize("name", [n for n in golden_models() if n in ("asia", "cancer", "child", "alarm", "hepar2")])
 def test_bp_mode_matches_reference_golden(name):
-    """BeliefPropagation(<our junction tree>).query of the unmodified reference vs the oracle BP."""
+    """BeliefPropagation(<our junction tree>).query of the unmodified reference vs the oracle BP: both iterate belief
+    updates until np.allclose accepts, so they agree to that stopping rule (fixed tolerance, no adjustment)."""
     g = load_golden(name)
     m = px.get_example_model(name)
     jt = JTStructure.from_model(m)
     bp = O.BP(jt.cliques, jt.edges, [O.Factor(c, p) for c, p in zip(jt.cliques, jt.potentials)])
     bp.calibrate()
-    net = O.Net(m)
     for case, q, want in g["bp"][:24]:
         ev_idx = {v: int(s) for v, s in zip(g["ev_vars"], g["ev_states"][case])}
         got = bp.query([q], ev_idx)
-        # both are the reference's iterate-until-allclose calibration; the exact closed form (all factors,
-        # no pruning) tells how far that stopping rule leaves each of them
-        exact = O.ve_query(net, [q], {v: m.states[v][s] for v, s in ev_idx.items()}, prune_model=False).values
-        tol = max(bp_reference_tolerance(want, exact), bp_reference_tolerance(got.values, exact))
-        assert tol <= 1e-6
-        assert rel_err(got.values, want) <= tol
+        assert rel_err(got.values, want) <= BP_QUERY_REFERENCE_RESIDUAL
 
 
 def test_bp_closed_form_equals_unpruned_ve():
