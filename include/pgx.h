@@ -74,6 +74,9 @@ extern "C" {
 
 #define PGX_OPT_VEC2 8         /* stepwise mode: two evidence sets per lane (16-byte loads) when B >= 64 (default 0) */
 
+#define PGX_OPT_STAGE 9        /* stepwise mode: GEMM-shaped two-operand steps run on the TMA-staged register-tile kernel
+                                  (pgx_stage.cuh; default 1) */
+
 #define PGX_INFO_N_STEPS 1
 #define PGX_INFO_OUT_ELEMS 2
 #define PGX_INFO_WS_ENTRIES 3
@@ -82,6 +85,7 @@ extern "C" {
 #define PGX_INFO_N_EV 6
 #define PGX_INFO_LAST_VARIANT 7 /* which fused kernel ran (PGX_OPT_FUSED_KERNEL numbering), 0 if stepwise */
 #define PGX_INFO_LAST_GRAPH 9    /* 1 if the most recent stepwise run was a CUDA-graph replay */
+#define PGX_INFO_LAST_STAGED_STEPS 10 /* steps the most recent stepwise run sent to the TMA-staged GEMM-tile kernel */
 #define PGX_INFO_N_LEVELS 8     /* dependency levels of the plan (0 when no offset tables were built) */
 
 typedef struct pgx_plan pgx_plan; /* opaque */
@@ -123,6 +127,10 @@ int pgx_profile_steps(pgx_plan* plan, const int32_t* ev_states, void* out, void*
 int pgx_profile_launches(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
                          int64_t B, void* stream, float* launch_ms, int32_t cap_launches, int32_t* step_launch,
                          int32_t n_steps, int32_t* n_launches);
+
+/* Host only (no GPU needed): the tiling the staged GEMM-tile kernel (pgx_stage.cuh) would use for one step record
+ * (layout in pgmpy_b200/plan.py). fields[12] = eligible, ax, ay, bx, by, ntx, nty, tiles, sc, swap, form, stage_elems. */
+int pgx_stage_pick(const int32_t* step_record, int32_t item_bytes, int32_t* fields, int64_t* smem_bytes);
 
 int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value);
 int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value);

@@ -10,8 +10,10 @@ LIB_PATH = os.environ.get("PGX_LIB", os.path.join(HERE, "libpgx.so"))  # PGX_LIB
 PGX_F64, PGX_F32 = 0, 1
 MODE_AUTO, MODE_STEPWISE, MODE_FUSED = 0, 1, 2
 OPT_MODE, OPT_FUSED_WARPS, OPT_USE_GRAPH, OPT_FUSED_KERNEL, OPT_STEP_KERNEL, OPT_REG_TILE, OPT_GEMM_TILE, OPT_VEC2 = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_STAGE = 9
 INFO_N_STEPS, INFO_OUT_ELEMS, INFO_WS_ENTRIES, INFO_LAST_LAUNCHES, INFO_LAST_MODE, INFO_N_EV = 1, 2, 3, 4, 5, 6
 INFO_LAST_VARIANT, INFO_N_LEVELS, INFO_LAST_GRAPH = 7, 8, 9
+INFO_LAST_STAGED_STEPS = 10
 FUSED_KERNELS = {"auto": 0, "generic": 1, "tables-smem": 2, "tables-global": 3}
 
 EXPORTS = (
@@ -21,6 +23,7 @@ EXPORTS = (
     "pgx_run_batch",
     "pgx_profile_steps",
     "pgx_profile_launches",
+    "pgx_stage_pick",
     "pgx_plan_set_option",
     "pgx_plan_get_info",
     "pgx_evidence_reduce",
@@ -81,6 +84,8 @@ def load():
         i32p, C.c_int32, i32p,
     ]
     lib.pgx_profile_launches.restype = C.c_int
+    lib.pgx_stage_pick.argtypes = [i32p, C.c_int32, i32p, C.POINTER(C.c_int64)]
+    lib.pgx_stage_pick.restype = C.c_int
     lib.pgx_plan_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
     lib.pgx_plan_set_option.restype = C.c_int
     lib.pgx_plan_get_info.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]

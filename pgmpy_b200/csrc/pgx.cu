@@ -24,6 +24,7 @@
 #include "../../include/pgx.h"
 #include "pgx_step.cuh"
 #include "pgx_fused.cuh"
+#include "pgx_stage.cuh"
 
 namespace {
 
@@ -1179,8 +1180,112 @@ struct LaunchGroup {
     size_t smem = 0;
     bool rtile = false;  // the group holds GEMM-shaped steps: use the register-tiled instantiation
     bool gemm = false;   // every step of the group goes to k_contract_gemm32 (2-D register tile)
+    bool stage = false;  // every step of the group goes to k_contract_stage (TMA-staged GEMM tiles)
     std::vector<int> step_ids;  // plan steps served by this launch (tracing: pgx_profile_launches)
 };
+
+// Host: can this step run on the staged GEMM-tile kernel, and with which tiling? (pgx_stage.cuh)
+static bool pick_stage(const int32_t* r, int64_t out_size, int64_t sum_size, size_t item_bytes, pgx::StageItem& it,
+                       size_t& smem_bytes) {
+    using namespace pgx;
+    const int A = r[0], S = r[1], K = r[2], flags = r[3];
+    if (K != 2 || flags != 0 || A < 1 || S < 1 || sum_size < 2 || sum_size > 4096 || out_size * sum_size < 2048) return false;
+    const int opw = OP_FIXED + A + S;
+    const int32_t* odims = r + STEP_FIXED;
+    const int32_t* ops = odims + A + S;
+    bool work[2];
+    for (int k = 0; k < 2; ++k) {
+        const int32_t* op = ops + k * opw;
+        if (op[3] != 0) return false;  // evidence-dependent operand: per-lane base, cannot be staged as rows
+        work[k] = (op[0] & 0xFF) == 1;
+    }
+    auto type_of = [&](int k, int ax, int ay) {
+        const int32_t* op = ops + k * opw;
+        return (op[OP_FIXED + ax] ? 1 : 0) | ((ay >= 0 && op[OP_FIXED + ay]) ? 2 : 0);
+    };
+    auto cnt = [](int t) { return t == 0 ? 1 : (t == 3 ? 16 : 4); };
+    // best (ax, ay, operand order): fewest shared-memory loads per useful multiply-add of a 4 x 4 register block
+    double best = 1e30;
+    int b_ax = -1, b_ay = -1, b_swap = 0, b_form = 0;
+    for (int ax = 0; ax < A; ++ax) {
+        if (odims[ax] < 2) continue;
+        for (int ay = -1; ay < A; ++ay) {
+            if (ay == ax || (ay >= 0 && odims[ay] < 2)) continue;
+            for (int sw = 0; sw < 2; ++sw) {
+                const int tp = type_of(sw, ax, ay), tq = type_of(1 - sw, ax, ay);
+                const int form = tp * 4 + tq;
+                if (!(form == 6 || form == 7 || form == 3 || form == 1 || form == 5)) continue;
+                if (ay < 0 && form != 1 && form != 5) continue;
+                const int ux = odims[ax] < 4 ? odims[ax] : 4;
+                const int uy = ay >= 0 ? (odims[ay] < 4 ? odims[ay] : 4) : 1;
+                const double loads = ay >= 0 ? cnt(tp) + cnt(tq) : (tp ? 4 : 1) + (tq ? 4 : 1);
+                // the math itself also takes issue slots for the padded block (16 or 4 multiply-adds)
+                const double score = (loads + 0.25 * (ay >= 0 ? 16 : 4)) / (ux * uy);
+                if (score < best) {
+                    best = score;
+                    b_ax = ax;
+                    b_ay = ay;
+                    b_swap = sw;
+                    b_form = form;
+                }
+            }
+        }
+    }
+    if (b_ax < 0 || best > 1.5) return false;  // the streaming kernel spends 2 loads per multiply-add
+    const int tp = b_form >> 2, tq = b_form & 3;
+    const int dX = odims[b_ax], dY = b_ay >= 0 ? odims[b_ay] : 1;
+    int64_t n_other = 1;
+    for (int a = 0; a < A; ++a)
+        if (a != b_ax && a != b_ay) n_other *= odims[a];
+    // register blocks per tile: fewest padded outputs + staged rows
+    static const int cand[][2] = {{2, 4}, {4, 2}, {2, 2}, {1, 4}, {4, 1}, {1, 8}, {8, 1}, {1, 2}, {2, 1}, {1, 1}, {2, 3}, {3, 2}, {1, 3}, {3, 1}, {1, 6}, {6, 1}};
+    double bc = 1e30;
+    int bx = 1, by = 1;
+    for (auto& c : cand) {
+        if (b_ay < 0 && c[1] != 1) continue;
+        const int64_t ntx = (dX + 4 * c[0] - 1) / (4 * c[0]), nty = (dY + 4 * c[1] - 1) / (4 * c[1]);
+        const int rows_p = work[b_swap] ? ((tp & 1) ? 4 * c[0] : 1) * ((tp & 2) ? 4 * c[1] : 1) : 0;
+        const int rows_q = work[1 - b_swap] ? ((tq & 1) ? 4 * c[0] : 1) * ((tq & 2) ? 4 * c[1] : 1) : 0;
+        const double cost = (double)(ntx * nty) * (1.5 * 16 * c[0] * c[1] + 8.0 * (rows_p + rows_q));
+        if (cost < bc) {
+            bc = cost;
+            bx = c[0];
+            by = c[1];
+        }
+    }
+    const int pitch_p = work[b_swap] ? 32 : 1, pitch_q = work[1 - b_swap] ? 32 : 1;
+    const int64_t slots_p = ((tp & 1) ? 4 * bx : 1) * ((tp & 2) ? 4 * by : 1);
+    const int64_t slots_q = ((tq & 1) ? 4 * bx : 1) * ((tq & 2) ? 4 * by : 1);
+    const int64_t per_s = slots_p * pitch_p + slots_q * pitch_q;  // elements per summed index
+    int64_t sc = (40 * 1024) / (per_s * (int64_t)item_bytes);
+    if (sc < 1) sc = 1;
+    if (sc > sum_size) sc = sum_size;
+    const int64_t n_chunks = (sum_size + sc - 1) / sc;
+    sc = (sum_size + n_chunks - 1) / n_chunks;
+    const int64_t p_elems = (slots_p * pitch_p * sc + 3) / 4 * 4;
+    const int64_t stage_elems = p_elems + (slots_q * pitch_q * sc + 3) / 4 * 4;
+    const int64_t rec_len = STEP_FIXED + A + S + 2 * opw;
+    smem_bytes = 128 + (size_t)(((rec_len + 3) & ~3) + ((2 * sum_size + 3) & ~3)) * 4 + 2 * (size_t)stage_elems * item_bytes;
+    if (smem_bytes > 200 * 1024) return false;
+    const int64_t ntx = (dX + 4 * bx - 1) / (4 * bx), nty = (dY + 4 * by - 1) / (4 * by);
+    const int64_t tiles = n_other * ntx * nty;
+    if (tiles > (1 << 24)) return false;
+    it.ax = b_ax;
+    it.ay = b_ay;
+    it.bx = bx;
+    it.by = by;
+    it.ntx = (int32_t)ntx;
+    it.nty = (int32_t)nty;
+    it.tiles = (int32_t)tiles;
+    it.sc = (int32_t)sc;
+    it.swap = b_swap;
+    it.form = b_form;
+    it.stage_elems = (int32_t)stage_elems;
+    it.p_elems = (int32_t)p_elems;
+    it.pad = 0;
+    if (const char* e = std::getenv("PGX_STAGE_DEBUG")) it.pad = std::atoi(e);  // tuning aid: 1 no math, 2 no copies
+    return true;
+}
 
 struct StepSchedule {
     int64_t B = 0;
@@ -1188,6 +1293,7 @@ struct StepSchedule {
     bool vec2 = false;  // tile groups use the two-evidence-sets-per-lane kernel (64 evidence sets per warp)
     std::vector<LaunchGroup> groups;
     TileItem* d_items = nullptr;
+    pgx::StageItem* d_stage_items = nullptr;
 };
 
 struct GraphEntry {
@@ -1226,6 +1332,7 @@ struct pgx_plan {
     int vec2 = 0;         // tile kernel with two evidence sets per lane when B >= 64 (PGX_OPT_VEC2); measured slower, opt-in
     int gemm_tile = 0;    // route GEMM-shaped steps to k_contract_gemm32 (PGX_OPT_GEMM_TILE); measured slower, opt-in
     int reg_tile = 0;     // register-tile GEMM-shaped steps (PGX_OPT_REG_TILE); measured neutral-to-slower, off by default
+    int stage = 1;        // GEMM-shaped two-operand steps go to the TMA-staged register-tile kernel (PGX_OPT_STAGE)
     int batch_levels = 1; // share one launch among the tile-eligible steps of a dependency level
     cudaEvent_t* prof_events = nullptr;  // set only inside pgx_profile_steps
     int step_kernel = 0;  // 0 = auto (tile-cooperative where possible), 1 = generic per-thread kernel only
@@ -1399,8 +1506,10 @@ void pgx_plan_destroy(pgx_plan* plan) {
     if (plan->d_pool) cudaFree(plan->d_pool);
     if (plan->d_micro) cudaFree(plan->d_micro);
     for (GraphEntry& g : plan->graphs) cudaGraphExecDestroy(g.exec);
-    for (StepSchedule& c : plan->schedules)
+    for (StepSchedule& c : plan->schedules) {
         if (c.d_items) cudaFree(c.d_items);
+        if (c.d_stage_items) cudaFree(c.d_stage_items);
+    }
     if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
     delete plan;
 }
@@ -1430,11 +1539,15 @@ int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
         case PGX_OPT_VEC2:
         case PGX_OPT_GEMM_TILE:
         case PGX_OPT_REG_TILE:
-            if (option == PGX_OPT_GEMM_TILE) plan->gemm_tile = value ? 1 : 0;
+        case PGX_OPT_STAGE:
+            if (option == PGX_OPT_STAGE) plan->stage = value ? 1 : 0;
+            else if (option == PGX_OPT_GEMM_TILE) plan->gemm_tile = value ? 1 : 0;
             else if (option == PGX_OPT_VEC2) plan->vec2 = value ? 1 : 0;
             else plan->reg_tile = value ? 1 : 0;
-            for (StepSchedule& c : plan->schedules)
+            for (StepSchedule& c : plan->schedules) {
                 if (c.d_items) cudaFree(c.d_items);
+                if (c.d_stage_items) cudaFree(c.d_stage_items);
+            }
             plan->schedules.clear();
             for (GraphEntry& g : plan->graphs) cudaGraphExecDestroy(g.exec);
             plan->graphs.clear();
@@ -1464,6 +1577,14 @@ int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value) {
         case PGX_INFO_LAST_VARIANT: *value = plan->last_variant; break;
         case PGX_INFO_LAST_GRAPH: *value = plan->last_graph; break;
         case PGX_INFO_N_LEVELS: *value = plan->micro.ok ? plan->micro.n_levels : 0; break;
+        case PGX_INFO_LAST_STAGED_STEPS: {
+            int64_t n = 0;
+            if (plan->last_mode == PGX_MODE_STEPWISE && plan->last_sched >= 0 && plan->last_sched < (int)plan->schedules.size())
+                for (const LaunchGroup& g : plan->schedules[plan->last_sched].groups)
+                    if (g.stage) n += g.n_items;
+            *value = n;
+            break;
+        }
         default: return fail(PGX_ERR_UNSUPPORTED, "unknown info key");
     }
     return PGX_OK;
@@ -1562,13 +1683,13 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
         // launch schedule for this batch size: tile-eligible steps of one dependency level share a launch
         StepSchedule* sched = nullptr;
         for (StepSchedule& c : pl->schedules)
-            if (c.B == B && c.step_kernel == pl->step_kernel + 4 * pl->batch_levels + 8 * pl->gemm_tile + 16 * pl->vec2 &&
+            if (c.B == B && c.step_kernel == pl->step_kernel + 4 * pl->batch_levels + 8 * pl->gemm_tile + 16 * pl->vec2 + 32 * pl->stage &&
                 c.dtype_size == (int)sizeof(T))
                 sched = &c;
         if (!sched) {
             StepSchedule ns;
             ns.B = B;
-            ns.step_kernel = pl->step_kernel + 4 * pl->batch_levels + 8 * pl->gemm_tile + 16 * pl->vec2;
+            ns.step_kernel = pl->step_kernel + 4 * pl->batch_levels + 8 * pl->gemm_tile + 16 * pl->vec2 + 32 * pl->stage;
             // 16-byte lanes when the batch is wide enough and 32-bit addressing applies (checked again at launch)
             ns.vec2 = pl->vec2 && pl->step_kernel == 0 && bt_log2 == 5 && B >= 64 && !pl->gemm_tile && !pl->reg_tile &&
                       ws_off0 + (size_t)pl->ws_entries * (size_t)ldb < (1ULL << 32) && pl->ws_entries < (1LL << 31);
@@ -1589,10 +1710,22 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
             };
             // per dependency level: one group of plain tile steps, one group of GEMM-shaped steps, generic steps alone
             LaunchGroup cur[2];
+            // ... and one group of steps for the TMA-staged GEMM-tile kernel
+            LaunchGroup cur_stage;
+            std::vector<StageItem> stage_items, pending_stage;
+            const bool stage_on = pl->stage && pl->step_kernel == 0 && bt_log2 == 5 && !ns.vec2 &&
+                                  ws_off0 + (size_t)pl->ws_entries * (size_t)ldb < (1ULL << 32) && pl->ws_entries < (1LL << 31);
             int cur_level = -1;
             auto flush_level = [&]() {
                 flush(cur[0]);
                 flush(cur[1]);
+                if (cur_stage.n_items > 0) {
+                    cur_stage.first_item = (int)stage_items.size();
+                    stage_items.insert(stage_items.end(), pending_stage.begin(), pending_stage.end());
+                    pending_stage.clear();
+                    ns.groups.push_back(cur_stage);
+                }
+                cur_stage = LaunchGroup();
             };
             for (size_t si = 0; si < pl->steps.size(); ++si) {
                 const StepInfo& s = pl->steps[si];
@@ -1608,6 +1741,25 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                                      s.out_size / n1 >= 3 && s.out_size * s.sum_size >= 4096;
                 if (s.level != cur_level || !pl->batch_levels) flush_level();
                 cur_level = s.level;
+                if (stage_on && tile_ok) {
+                    StageItem sit;
+                    size_t sm = 0;
+                    if (pick_stage(srec, s.out_size, s.sum_size, sizeof(T), sit, sm)) {
+                        const int64_t n_blocks = (int64_t)sit.tiles * b_tiles;
+                        if ((int64_t)cur_stage.n_blocks + n_blocks < (1LL << 30)) {
+                            sit.rec_off = s.rec_off;
+                            sit.rec_len = s.rec_len;
+                            sit.blk_begin = cur_stage.n_blocks;
+                            pending_stage.push_back(sit);
+                            cur_stage.stage = true;
+                            cur_stage.step_ids.push_back((int)si);
+                            cur_stage.n_items += 1;
+                            cur_stage.n_blocks += (int)n_blocks;
+                            cur_stage.smem = std::max(cur_stage.smem, sm);
+                            continue;
+                        }
+                    }
+                }
                 if (!tile_ok) {
                     flush_level();
                     LaunchGroup g;
@@ -1653,8 +1805,13 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                 PGX_CUDA(cudaMalloc((void**)&ns.d_items, items.size() * sizeof(TileItem)));
                 PGX_CUDA(cudaMemcpy(ns.d_items, items.data(), items.size() * sizeof(TileItem), cudaMemcpyHostToDevice));
             }
+            if (!stage_items.empty()) {
+                PGX_CUDA(cudaMalloc((void**)&ns.d_stage_items, stage_items.size() * sizeof(StageItem)));
+                PGX_CUDA(cudaMemcpy(ns.d_stage_items, stage_items.data(), stage_items.size() * sizeof(StageItem), cudaMemcpyHostToDevice));
+            }
             if (pl->schedules.size() >= 8) {
                 if (pl->schedules.front().d_items) cudaFree(pl->schedules.front().d_items);
+                if (pl->schedules.front().d_stage_items) cudaFree(pl->schedules.front().d_stage_items);
                 pl->schedules.erase(pl->schedules.begin());
                 for (GraphEntry& g : pl->graphs) cudaGraphExecDestroy(g.exec);  // graphs reference the item tables
                 pl->graphs.clear();
@@ -1692,6 +1849,12 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                     else
                         PGX_LAUNCH_STEP(MAX_OPS);
 #undef PGX_LAUNCH_STEP
+                } else if (g.stage) {
+                    if (g.smem > 48 * 1024)
+                        cudaFuncSetAttribute(k_contract_stage<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+                    k_contract_stage<T><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, sched->d_stage_items + g.first_item,
+                                                                                  g.n_items, ws_all, ws_all, (uint32_t)ws_off0, B,
+                                                                                  (uint32_t)ldb);
                 } else {
                     const TileItem* d_it = sched->d_items + g.first_item;
 #define PGX_LAUNCH_TILE(MK, RT)                                                                                            \
@@ -1877,6 +2040,17 @@ int pgx_profile_launches(pgx_plan* plan, const int32_t* ev_states, void* out, vo
         launch_ms[g] = ms[g];
         for (int si : sc.groups[g].step_ids) step_launch[si] = (int32_t)g;
     }
+    return PGX_OK;
+}
+
+int pgx_stage_pick(const int32_t* step_record, int32_t item_bytes, int32_t* fields, int64_t* smem_bytes) {
+    if (!step_record || !fields || !smem_bytes || (item_bytes != 4 && item_bytes != 8)) return fail(PGX_ERR_INVALID, "bad argument");
+    pgx::StageItem it{};
+    size_t sm = 0;
+    const bool ok = pick_stage(step_record, ld_i64(step_record + 4), ld_i64(step_record + 6), (size_t)item_bytes, it, sm);
+    *smem_bytes = (int64_t)sm;
+    const int32_t f[12] = {ok ? 1 : 0, it.ax, it.ay, it.bx, it.by, it.ntx, it.nty, it.tiles, it.sc, it.swap, it.form, it.stage_elems};
+    for (int i = 0; i < 12; ++i) fields[i] = f[i];
     return PGX_OK;
 }
 

@@ -102,8 +102,16 @@ class CompiledPlan:
     def set_reg_tile(self, enabled: bool = True):
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_REG_TILE, 1 if enabled else 0))
 
+    def set_stage(self, enabled: bool = True):
+        """GEMM-shaped two-operand steps on the TMA-staged register-tile kernel (default on)."""
+        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_STAGE, 1 if enabled else 0))
+
     def set_graph(self, enabled: bool = True):
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_USE_GRAPH, 1 if enabled else 0))
+
+    @property
+    def last_staged_steps(self) -> int:
+        return self.info(N.INFO_LAST_STAGED_STEPS)
 
     @property
     def last_graph(self) -> bool:

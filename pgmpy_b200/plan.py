@@ -203,6 +203,7 @@ class PlanBuilder:
         self._const_chunks: List[np.ndarray] = []
         self._const_len = 0
         self._const_cache: Dict[int, Table] = {}
+        self._memo: Dict[tuple, Table] = {}  # contraction -> its result table (common-subexpression reuse)
 
     # ---- tables ----------------------------------------------------------------------------
     def add_const(self, vars_: Sequence[Hashable], values: np.ndarray, key=None) -> Table:
@@ -267,6 +268,17 @@ class PlanBuilder:
         range is cut in two (partial sums over an enlarged output, then a small reduce) so the grid has work."""
         out_vars = tuple(out_vars)
         ops = list(operands)
+        # identical contractions are computed once (tables are written once and never change): the distribute pass
+        # re-derives many of the partial products the collect pass already built
+        memo_key = (tuple(sorted(t.tid for t in ops)), tuple(t.tid for t in divisors), out_vars, bool(reduce_max))
+        hit = self._memo.get(memo_key)
+        if hit is not None:
+            return hit
+        result = self._contract(ops, out_vars, divisors, reduce_max, level, optimize, split)
+        self._memo[memo_key] = result
+        return result
+
+    def _contract(self, ops, out_vars, divisors, reduce_max, level, optimize, split) -> Table:
         needed_later = set(out_vars)
         for d in divisors:
             needed_later |= set(self._free(d))
@@ -280,8 +292,14 @@ class PlanBuilder:
             return sc
 
         if optimize and len(ops) > 2 and self.reassociate:
+            # Greedy pairwise re-association by operand loads. Evaluating the product directly costs one load per
+            # operand per entry of the joint scope J: J * n. Multiplying two operands first costs 2 loads per entry of
+            # THEIR joint scope, a store and a re-load of what is kept, and leaves n - 1 operands over a joint scope that
+            # has lost the variables summed away in the pair step.
             while len(ops) > 2:
-                final_joint = self._prod(union_scope(ops))
+                scope_all = union_scope(ops)
+                final_joint = self._prod(scope_all)
+                direct = final_joint * len(ops)
                 count: Dict[Hashable, int] = {}
                 for t in ops:
                     for v in self._free(t):
@@ -292,15 +310,19 @@ class PlanBuilder:
                     si = set(fi)
                     for j in range(i + 1, len(ops)):
                         fj = self._free(ops[j])
+                        sj = set(fj)
                         u = fi + [v for v in fj if v not in si]
                         cost = self._prod(u)
-                        if 2 * cost >= final_joint:
+                        if 2 * cost >= direct:
                             continue
-                        keep = [v for v in u if v in needed_later or count[v] > (1 if v in si else 0) + (1 if v in fj else 0)]
-                        key = (self._prod(keep), cost)
+                        keep = [v for v in u if v in needed_later or count[v] > (1 if v in si else 0) + (1 if v in sj else 0)]
+                        kept = self._prod(keep)
+                        rest_joint = final_joint // (cost // kept)
+                        total = 2 * cost + 2 * kept + rest_joint * (len(ops) - 1)
+                        key = (total, kept, cost)
                         if best is None or key < best[0]:
                             best = (key, i, j, keep)
-                if best is None:
+                if best is None or best[0][0] >= direct:
                     break
                 _, i, j, keep = best
                 merged = self.contract([ops[i], ops[j]], keep, reduce_max=reduce_max, level=level, optimize=False)
@@ -351,6 +373,36 @@ class PlanBuilder:
             if t.kind == KIND_WORK:
                 t.last_step = max(t.last_step, idx)
         return out
+
+    # ---- trial builds ------------------------------------------------------------------------
+    # cost model of a step sequence, per evidence set: HBM time of its work-table traffic + issue time of its operand
+    # loads (rates measured on B200 for the step kernels: ~4.5 TB/s streaming, ~3e12 operand loads/s)
+    COST_BYTES_PER_NS = 4500.0
+    COST_LOADS_PER_NS = 3000.0
+
+    def mark(self):
+        """Snapshot for rollback(): lets the planner build a candidate step sequence, price it, and undo it."""
+        return (len(self.tables), len(self.steps), len(self.segments), len(self._const_chunks), self._const_len,
+                dict(self._const_cache), dict(self._memo), [t.last_step for t in self.tables])
+
+    def rollback(self, mk) -> None:
+        n_t, n_s, n_g, n_c, c_len, c_cache, memo, last = mk
+        del self.tables[n_t:], self.steps[n_s:], self.segments[n_g:], self._const_chunks[n_c:]
+        self._const_len = c_len
+        self._const_cache = dict(c_cache)  # copies: the same mark may be rolled back to more than once
+        self._memo = dict(memo)
+        for t, l in zip(self.tables, last):
+            t.last_step = l
+
+    def cost_since(self, mk) -> float:
+        """Estimated ns per evidence set of the steps added since mark()."""
+        loads = 0
+        nbytes = 0
+        for st in self.steps[mk[1]:]:
+            joint = st.out.size * self._prod(st.sum_vars)
+            loads += joint * max(1, len(st.operands))
+            nbytes += 8 * (st.out.size + sum(t.size for t, _ in st.operands if t.kind == KIND_WORK))
+        return nbytes / self.COST_BYTES_PER_NS + loads / self.COST_LOADS_PER_NS
 
     def emit(self, table: Table, normalize: bool, vars_: Sequence[Hashable] = None) -> Segment:
         if table.kind != KIND_WORK:

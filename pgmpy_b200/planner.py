@@ -269,11 +269,18 @@ def compile_ve_multi_plan(
 # junction-tree (BP mode) plans
 # ---------------------------------------------------------------------------------------------
 class JTStructure:
-    """Rooted junction tree + clique potentials, built once per model and shared by all signatures."""
+    """Rooted junction tree + clique potentials, built once per model and shared by all signatures.
 
-    def __init__(self, cliques, edges, potentials, card, states):
+    A clique potential is kept in two forms: `factors[i]`, the list of (scope, table) assigned to clique i — for a
+    Bayesian network the CPDs themselves, never multiplied out — and `potentials[i]`, their dense product over the
+    clique (what the reference builds at pgmpy/models/DiscreteMarkovNetwork.py:598-629), computed on first use. The
+    big cliques of diabetes / munin (1e5 .. 2.7e6 entries) hold one 3-variable CPD or none at all: plans that multiply
+    the factors into the messages (`compile_jt_plan(factorized=True)`) never touch a clique-sized constant table."""
+
+    def __init__(self, cliques, edges, potentials, card, states, factors=None):
         self.cliques = [tuple(c) for c in cliques]
-        self.potentials = potentials  # list of ndarray shaped by clique dims
+        self._potentials = potentials  # list of ndarray shaped by clique dims, or None until first use
+        self.factors = factors if factors is not None else [[(tuple(c), p)] for c, p in zip(self.cliques, potentials)]
         self.card = dict(card)
         self.states = states
         n = len(self.cliques)
@@ -305,6 +312,16 @@ class JTStructure:
             for y in self.children[x]:
                 self.height[x] = max(self.height[x], self.height[y] + 1)
 
+    @property
+    def potentials(self):
+        if self._potentials is None:
+            pots = []
+            for c, mine in zip(self.cliques, self.factors):
+                dims = [self.card[v] for v in c]
+                pots.append(np.ones(dims) * _product_tables(mine, c) if mine else np.ones(dims))
+            self._potentials = pots
+        return self._potentials
+
     def _centre(self) -> int:
         n = len(self.cliques)
         if n == 1:
@@ -334,12 +351,10 @@ class JTStructure:
         card = model.get_cardinality()
         cpds = model.get_cpds()
         owner = assign_factors(cliques, [c.variables for c in cpds], card)
-        pots = []
-        for i, c in enumerate(cliques):
-            mine = [(cpd.variables, cpd.values) for cpd, o in zip(cpds, owner) if o == i]
-            dims = [card[v] for v in c]
-            pots.append(np.ones(dims) * _product_tables(mine, c) if mine else np.ones(dims))
-        return cls(cliques, edges, pots, card, model.states)
+        factors = [[] for _ in cliques]
+        for cpd, o in zip(cpds, owner):
+            factors[o].append((tuple(cpd.variables), np.asarray(cpd.values, dtype=np.float64)))
+        return cls(cliques, edges, None, card, model.states, factors=factors)
 
     @classmethod
     def from_junction_tree(cls, jt: JunctionTree) -> "JTStructure":
@@ -369,6 +384,16 @@ class JTStructure:
         return cls(cliques, edges, pots, card, jt.states)
 
 
+def plan_cost(plan: Plan) -> float:
+    """Estimated ns per evidence set (PlanBuilder's cost model: HBM time of the work-table traffic + issue time of the
+    operand loads). Used to choose between plan variants of the same query."""
+    loads = plan.operand_loads()
+    nbytes = 0
+    for st in plan.steps:
+        nbytes += 8 * (st.out.size + sum(t.size for t, _ in st.operands if t.kind == 1))
+    return nbytes / PlanBuilder.COST_BYTES_PER_NS + loads / PlanBuilder.COST_LOADS_PER_NS
+
+
 def compile_jt_plan(
     jt: JTStructure,
     evidence_vars: Sequence[Hashable] = (),
@@ -377,6 +402,7 @@ def compile_jt_plan(
     emit_beliefs: bool = False,
     distribute: str = "auto",
     reduce_max: bool = False,
+    factorized="auto",
 ) -> Plan:
     """Two-pass message passing on the rooted junction tree for one evidence-variable signature.
 
@@ -389,20 +415,61 @@ def compile_jt_plan(
 
     `variables=None` means every unobserved variable of the tree (all-marginals query).
     `emit_beliefs=True` emits the calibrated clique beliefs and sepset beliefs instead (un-normalised,
-    like get_clique_beliefs/get_sepset_beliefs, :750-768)."""
-    if distribute == "auto" and not emit_beliefs:
-        # Shafer-Shenoy keeps the workspace smallest (messages only: fits shared memory for alarm-class models);
-        # belief-update wins when high-degree cliques would recompute their product once per neighbour.
-        cands = [compile_jt_plan(jt, evidence_vars, variables, normalize, False, d, reduce_max) for d in ("ss", "belief")]
-        cost = [p.operand_loads() for p in cands]
-        return cands[0] if cost[0] <= 1.2 * cost[1] else cands[1]
+    like get_clique_beliefs/get_sepset_beliefs, :750-768).
+
+    `factorized`: psi_i enters every product as the LIST of factors assigned to the clique (the CPDs) instead of one
+    clique-sized table, so the re-association of PlanBuilder.contract can multiply a 3-variable CPD into a small
+    message before anything clique-sized is touched, and a clique without factors costs nothing at all.
+    `distribute`: "ss" | "belief" | "divide" as above, "adaptive" = per clique, whichever of Shafer-Shenoy messages
+    and materialised belief + marginalisation lattice the cost model prices lower; "auto" compiles the candidate
+    strategies and returns the cheapest plan."""
+    if (distribute == "auto" or factorized == "auto") and not emit_beliefs:
+        # dense potentials + Shafer-Shenoy keeps the workspace smallest (messages only: fits shared memory for
+        # alarm-class models); factor lists + per-clique choice wins on the big-clique models
+        dense_ok = sum(int(np.prod([jt.card[v] for v in c], dtype=np.int64)) for c in jt.cliques) <= (1 << 22)
+        fz = [False, True] if factorized == "auto" else [bool(factorized)]
+        if not dense_ok and factorized == "auto":
+            fz = [True]
+        cands = []
+        for f in fz:
+            for d in (("ss", "belief", "adaptive") if distribute == "auto" else (distribute,)):
+                if d == "adaptive" and not f:
+                    continue
+                cands.append(compile_jt_plan(jt, evidence_vars, variables, normalize, False, d, reduce_max, f))
+        cost = [plan_cost(p) for p in cands]
+        # stay with the first (dense, Shafer-Shenoy) candidate unless another one is clearly cheaper
+        best = min(range(len(cands)), key=lambda i: cost[i])
+        return cands[0] if cost[0] <= 1.2 * cost[best] else cands[best]
+    factorized = bool(factorized) if factorized != "auto" else False
+    if distribute == "auto":
+        distribute = "belief"  # emit_beliefs materialises every belief anyway
     ev = list(evidence_vars)
     evset = set(ev)
     card = jt.card
     b = PlanBuilder(card, ev)
     n = len(jt.cliques)
     free = [tuple(v for v in c if v not in evset) for c in jt.cliques]
-    psi = [b.add_const(jt.cliques[i], jt.potentials[i]) for i in range(n)]
+    if factorized:
+        psi: List[List[Table]] = []
+        for i in range(n):
+            mine = [b.add_const(sc, vals) for sc, vals in jt.factors[i] if not all(v in evset for v in sc)]
+            psi.append(mine)
+    else:
+        psi = [[b.add_const(jt.cliques[i], jt.potentials[i])] for i in range(n)]
+    ones: Dict[Hashable, Table] = {}
+
+    def covered(ops, need):
+        """operands + all-ones vectors for the variables of `need` that no operand mentions (a clique variable whose
+        only factors live in other cliques enters this product through broadcasting)"""
+        have = set(v for t in ops for v in t.vars)
+        extra = []
+        for v in need:
+            if v not in have:
+                t = ones.get(v)
+                if t is None or t.tid >= len(b.tables) or b.tables[t.tid] is not t:  # (a rolled-back trial may have made it)
+                    ones[v] = b.add_const([v], np.ones(card[v]))
+                extra.append(ones[v])
+        return list(ops) + extra
 
     def sep(i, j):
         sj = set(jt.cliques[j])
@@ -420,8 +487,8 @@ def compile_jt_plan(
         p = jt.parent[i]
         if p < 0:
             continue
-        ops = [psi[i]] + [up[c] for c in jt.children[i]]
-        up[i] = b.contract(ops, sep(i, p), level=jt.height[i], reduce_max=reduce_max)
+        ops = psi[i] + [up[c] for c in jt.children[i]]
+        up[i] = b.contract(covered(ops, sep(i, p)), sep(i, p), level=jt.height[i], reduce_max=reduce_max)
     base_level = max(jt.height) + 1
     down: Dict[int, Table] = {}
     belief: Dict[int, Table] = {}
@@ -439,13 +506,11 @@ def compile_jt_plan(
             return False
         if distribute == "divide":
             return len(jt.children[i]) >= 1
-        return len(jt.nb[i]) >= 3 and len(jt.children[i]) >= 2  # "belief" (and "auto" when it resolves to it)
+        return len(jt.nb[i]) >= 3 and len(jt.children[i]) >= 2  # "belief"
 
-    for i in jt.pre:
-        lvl = base_level + 2 * jt.depth[i]
-        if want_belief(i):
-            belief[i] = b.contract([psi[i]] + incoming(i), free[i], level=lvl)
-        if i in belief and fsize(free[i]) >= 4096 and len(jt.children[i]) >= 2:
+    def messages_from_belief(i, lvl):
+        belief[i] = b.contract(covered(psi[i] + incoming(i), free[i]), free[i], level=lvl)
+        if fsize(free[i]) >= 4096 and len(jt.children[i]) >= 2:
             # big belief, several children: marginalisation lattice. Child sepsets are served largest first, each from
             # the smallest table already summed whose scope contains it (sum_{C \ S_a} = sum_{S_b \ S_a} sum_{C \ S_b}
             # when S_a is inside S_b), so a 2.7 M-entry munin belief is swept once or twice instead of once per
@@ -466,12 +531,34 @@ def compile_jt_plan(
                 undivided = b.contract([src], s_c, level=lvl + 1, reduce_max=reduce_max)
                 done.append((s_c, undivided))
                 down[c] = b.contract([undivided], s_c, divisors=[up[c]], level=lvl + 1, reduce_max=reduce_max)
-            continue
+            return
         for c in jt.children[i]:
-            if i in belief:
-                down[c] = b.contract([belief[i]], sep(i, c), divisors=[up[c]], level=lvl + 1, reduce_max=reduce_max)
-            else:
-                down[c] = b.contract([psi[i]] + incoming(i, exclude=c), sep(i, c), level=lvl + 1, reduce_max=reduce_max)
+            down[c] = b.contract([belief[i]], sep(i, c), divisors=[up[c]], level=lvl + 1, reduce_max=reduce_max)
+
+    def messages_shafer_shenoy(i, lvl):
+        for c in jt.children[i]:
+            ops = psi[i] + incoming(i, exclude=c)
+            down[c] = b.contract(covered(ops, sep(i, c)), sep(i, c), level=lvl + 1, reduce_max=reduce_max)
+
+    for i in jt.pre:
+        lvl = base_level + 2 * jt.depth[i]
+        if distribute == "adaptive" and not emit_beliefs:
+            if not jt.children[i]:
+                continue
+            mk = b.mark()
+            messages_shafer_shenoy(i, lvl)
+            cost_ss = b.cost_since(mk)
+            b.rollback(mk)
+            messages_from_belief(i, lvl)
+            if cost_ss <= b.cost_since(mk):
+                b.rollback(mk)
+                belief.pop(i, None)
+                messages_shafer_shenoy(i, lvl)
+            continue
+        if want_belief(i):
+            messages_from_belief(i, lvl)
+        else:
+            messages_shafer_shenoy(i, lvl)
     final_level = base_level + 2 * (max(jt.depth) + 1)
 
     if emit_beliefs:
@@ -525,7 +612,7 @@ def compile_jt_plan(
         elif i in belief:
             result[v] = b.contract([belief[i]], [v], level=final_level)
         else:
-            result[v] = b.contract([psi[i]] + incoming(i), [v], level=final_level)
+            result[v] = b.contract(covered(psi[i] + incoming(i), [v]), [v], level=final_level)
 
     def halve(table: Table, scope: List[Hashable], needed: List[Hashable]):
         """All single-variable marginals of `needed` out of one big table in ~2 passes over it (each half of the
@@ -549,13 +636,13 @@ def compile_jt_plan(
                 halve(b.contract([table], part, level=final_level), list(part), sub_needed)
 
     for i, vs in from_clique.items():
-        src = belief[i] if i in belief else b.contract([psi[i]] + incoming(i), free[i], level=final_level)
+        src = belief[i] if i in belief else b.contract(covered(psi[i] + incoming(i), free[i]), free[i], level=final_level)
         halve(src, list(free[i]), vs)
     for v in variables:
         b.emit(result[v], normalize, [v])
     return b.finalize(
         {"mode": "jt", "evidence_vars": tuple(ev), "variables": tuple(variables), "root": jt.root, "n_cliques": n,
-         "distribute": distribute}
+         "distribute": distribute, "factorized": factorized}
     )
 
 

@@ -148,6 +148,29 @@ def test_bp_marginals_batch_vs_reference_bp_query(torch_cuda, name):
     assert worst <= BP_QUERY_REFERENCE_RESIDUAL, worst
 
 
+@pytest.mark.parametrize("name,B", [("pathfinder", 40), ("diabetes", 96), ("munin", 64)])
+def test_staged_gemm_tile_kernel_matches(torch_cuda, name, B):
+    """GEMM-shaped two-operand steps on the TMA-staged register-tile kernel (pgx_stage.cuh) vs the streaming tile kernel
+    (itself pinned to the oracle and the reference goldens), incl. a partial last tile of evidence sets; pathfinder also
+    against the numpy plan interpreter."""
+    m = px.get_example_model(name)
+    jt = JTStructure.from_model(m)
+    ev_vars, states = sample_evidence(m, B, 8, seed=3)
+    plan = compile_jt_plan(jt, ev_vars)
+    cp = _engine()(plan)
+    cp.set_mode("stepwise")
+    cp.set_stage(False)
+    base = cp.run_host(states)
+    assert cp.last_staged_steps == 0
+    cp.set_stage(True)
+    got = cp.run_host(states)
+    assert cp.last_staged_steps > 0, "no step was routed to the staged kernel"
+    assert np.isfinite(got).all()
+    assert rel_err(got, base) <= 1e-13
+    if name == "pathfinder":
+        assert rel_err(got, run_plan(plan.pool, plan.const_blob, states)) <= 1e-12
+
+
 @pytest.mark.parametrize("name", ["pathfinder", "munin", "diabetes"])
 def test_large_models_stepwise_vs_oracle(torch_cuda, name):
     """HBM-resident clique tables: stepwise kernels vs the numpy interpreter on a small batch."""
