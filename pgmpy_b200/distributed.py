@@ -50,6 +50,25 @@ def gather_posteriors(local, total_rows: int = None, group=None):
     return out
 
 
+def gather_posteriors_to_root(local, dst: int = 0, group=None):
+    """Gather the per-rank posterior rows [B_r, out_elems] on rank `dst` only (rank order; equal shards): every other
+    rank sends its shard once over NVLink and receives nothing — the all-gather above moves world x more bytes to give
+    every rank a copy nobody asked for. Returns [sum B_r, out_elems] on `dst`, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if rank == dst:
+        full = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+        dist.gather(local.contiguous(), gather_list=list(full.unbind(0)), dst=dst, group=group)
+        return full.view(world * local.shape[0], *local.shape[1:])
+    dist.gather(local.contiguous(), gather_list=None, dst=dst, group=group)
+    return None
+
+
 def bind_process_to_gpu_numa(device_index: int):
     """Pin this process to the CPUs local to its GPU (PCIe root / NUMA node) so that pinned host buffers are
     first-touched on the right node; with 8 ranks streaming posteriors back to the host this decides whether the

@@ -431,15 +431,23 @@ def compile_jt_plan(
         if not dense_ok and factorized == "auto":
             fz = [True]
         cands = []
+        # a hub clique (pathfinder: 64 neighbours) makes pure Shafer-Shenoy quadratic in its degree: not a candidate
+        hub = max(len(x) for x in jt.nb) > 12
         for f in fz:
             for d in (("ss", "belief", "adaptive") if distribute == "auto" else (distribute,)):
                 if d == "adaptive" and not f:
                     continue
+                if d == "ss" and hub and distribute == "auto":
+                    continue
                 cands.append(compile_jt_plan(jt, evidence_vars, variables, normalize, False, d, reduce_max, f))
         cost = [plan_cost(p) for p in cands]
-        # stay with the first (dense, Shafer-Shenoy) candidate unless another one is clearly cheaper
         best = min(range(len(cands)), key=lambda i: cost[i])
-        return cands[0] if cost[0] <= 1.2 * cost[best] else cands[best]
+        # stay with the (dense, Shafer-Shenoy) candidate — smallest workspace, every step on the fused kernel's fast
+        # path — unless another one is clearly cheaper
+        first = cands[0].meta
+        if first["distribute"] == "ss" and not first["factorized"] and cost[0] <= 1.2 * cost[best]:
+            return cands[0]
+        return cands[best]
     factorized = bool(factorized) if factorized != "auto" else False
     if distribute == "auto":
         distribute = "belief"  # emit_beliefs materialises every belief anyway
@@ -544,6 +552,9 @@ def compile_jt_plan(
         lvl = base_level + 2 * jt.depth[i]
         if distribute == "adaptive" and not emit_beliefs:
             if not jt.children[i]:
+                continue
+            if len(jt.nb[i]) > 12:  # hub clique: one belief serves every neighbour
+                messages_from_belief(i, lvl)
                 continue
             mk = b.mark()
             messages_shafer_shenoy(i, lvl)

@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 import pgmpy_b200 as px
 from oracle.plan_exec import run_plan
-from pgmpy_b200.distributed import gather_posteriors, shard_range, shard_rows
+from pgmpy_b200.distributed import gather_posteriors, gather_posteriors_to_root, shard_range, shard_rows
 from pgmpy_b200.evidence import sample_evidence
 from pgmpy_b200.planner import JTStructure, compile_jt_plan
 
@@ -39,6 +39,12 @@ def _worker(rank, world, port, n, out_path):
     full = gather_posteriors(local, total_rows=n)
     if rank == 0:
         np.save(out_path, full.numpy())
+    if n % world == 0:
+        # gather-to-root (what bench.py times at N > 1): only rank 0 receives, in rank order
+        rooted = gather_posteriors_to_root(local, dst=0)
+        assert (rooted is None) == (rank != 0)
+        if rank == 0:
+            assert torch.equal(rooted, full)
     dist.barrier()
     dist.destroy_process_group()
 
