@@ -6,7 +6,7 @@ TEST INFRASTRUCTURE; run in the build container only (needs /root/reference):
 
 Each model is loaded with the reference's own reader (`pgmpy.utils.get_example_model`,
 /root/reference/pgmpy/utils/utils.py:16 -> readwrite/BIF.py:361) and written to
-`tests/golden/models/<name>.npz` as: a JSON header (node order, edges, per-CPD variable order =
+`pgmpy_b200/data/models/<name>.npz` as: a JSON header (node order, edges, per-CPD variable order =
 child first then parents in BIF order, cardinalities, state names) + one packed fp64 value blob in
 the reference's C-order layout (DiscreteFactor.py:91-127). No reference source is copied.
 """
@@ -17,7 +17,7 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-OUT_DIR = os.path.join(os.path.dirname(HERE), "tests", "golden", "models")
+OUT_DIR = os.path.join(os.path.dirname(HERE), "pgmpy_b200", "data", "models")
 DEFAULT = ["asia", "cancer", "sachs", "child", "alarm", "hepar2", "win95pts", "pathfinder", "munin", "diabetes"]
 
 

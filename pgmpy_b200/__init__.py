@@ -7,6 +7,7 @@ sm_100a CUDA kernels behind a C-ABI (`libpgx.so`, include/pgx.h) execute it over
 independent evidence sets. There is no CPU fallback: without the CUDA library every compute
 call raises.
 """
+from .config import config
 from .factors import DiscreteFactor, TabularCPD
 from .models import DiscreteBayesianNetwork, JunctionTree, get_example_model, from_pgmpy
 
@@ -17,6 +18,7 @@ __all__ = [
     "JunctionTree",
     "get_example_model",
     "from_pgmpy",
+    "config",
     "VariableElimination",
     "BeliefPropagation",
 ]

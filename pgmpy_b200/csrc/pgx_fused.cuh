@@ -230,42 +230,47 @@ __device__ __forceinline__ void micro_chunk_fast(const int32_t* __restrict__ mp,
             for (int j = 0; j < n_ev; ++j) evo[k] += evs[__ldg(pairs + 2 * j) * FUSED_LANES + lane] * __ldg(pairs + 2 * j + 1);
         }
     }
-    // Two output entries per iteration: a step never reads what it writes, but loads and stores go through the same
-    // pointer, so the compiler may not hoist the loads of entry o + 1 above the store of entry o. Doing both entries
-    // before either store doubles the independent loads in flight per warp (the kernel is latency bound: ~50 % issue).
+    // OU output entries per iteration: a step never reads what it writes, but loads and stores go through the same
+    // pointer, so the compiler may not hoist the loads of entry o + 1 above the store of entry o. Doing OU entries
+    // before any store multiplies the independent loads in flight per warp (the kernel is latency bound: ~50 % issue)
+    // and shares every offset-table read among them.
+    constexpr int OU = (K <= 2) ? 4 : ((K == 3) ? 3 : 2);
     int o = o0;
-    for (; o + 2 <= o0 + n_o; o += 2) {
+    for (; o + OU <= o0 + n_o; o += OU) {
         const int32_t* ot = otab + o * K;
-        int32_t b0[K], b1[K];
+        int32_t bo[OU][K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int32_t e = (k < NC ? evo[k < NC ? k : 0] : 0);
-            b0[k] = __ldg(ot + k) + e;
-            b1[k] = __ldg(ot + K + k) + e;
+#pragma unroll
+            for (int u = 0; u < OU; ++u) bo[u][k] = __ldg(ot + u * K + k) + e;
         }
-        T acc0 = (T)0, acc1 = (T)0;
+        T acc[OU];
+#pragma unroll
+        for (int u = 0; u < OU; ++u) acc[u] = (T)0;
         const int32_t* st = stab;
 #pragma unroll 2
         for (int s = 0; s < sum_size; ++s, st += K) {
-            T p0, p1;
+            T pr[OU];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int32_t so = __ldg(st + k);
-                const int32_t f0 = b0[k] + so, f1 = b1[k] + so;
-                const T v0 = (k < NC) ? __ldg(cst + f0) : (SMEM ? wsb[f0 * FUSED_LANES] : wsb[(int64_t)f0 * pitch]);
-                const T v1 = (k < NC) ? __ldg(cst + f1) : (SMEM ? wsb[f1 * FUSED_LANES] : wsb[(int64_t)f1 * pitch]);
-                p0 = (k == 0) ? v0 : p0 * v0;
-                p1 = (k == 0) ? v1 : p1 * v1;
+#pragma unroll
+                for (int u = 0; u < OU; ++u) {
+                    const int32_t f = bo[u][k] + so;
+                    const T v = (k < NC) ? __ldg(cst + f) : (SMEM ? wsb[f * FUSED_LANES] : wsb[(int64_t)f * pitch]);
+                    pr[u] = (k == 0) ? v : pr[u] * v;
+                }
             }
-            acc0 += p0;
-            acc1 += p1;
+#pragma unroll
+            for (int u = 0; u < OU; ++u) acc[u] += pr[u];
         }
-        if (SMEM) {
-            wsb[(out_off + o) * FUSED_LANES] = acc0;
-            wsb[(out_off + o + 1) * FUSED_LANES] = acc1;
-        } else {
-            wsb[(int64_t)(out_off + o) * pitch] = acc0;
-            wsb[(int64_t)(out_off + o + 1) * pitch] = acc1;
+#pragma unroll
+        for (int u = 0; u < OU; ++u) {
+            if (SMEM)
+                wsb[(out_off + o + u) * FUSED_LANES] = acc[u];
+            else
+                wsb[(int64_t)(out_off + o + u) * pitch] = acc[u];
         }
     }
     for (; o < o0 + n_o; ++o) {

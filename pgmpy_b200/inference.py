@@ -17,6 +17,7 @@ from typing import Dict, Hashable, List, Optional, Sequence
 
 import numpy as np
 
+from .config import config, default_dtype, logger, normalize_dtype
 from .engine import CompiledPlan, require_cuda
 from .factors import DiscreteFactor, TabularCPD
 from .models import DiscreteBayesianNetwork, JunctionTree, from_pgmpy, junction_tree_from_pgmpy
@@ -37,7 +38,9 @@ def _as_bn(model):
 
 
 class _Inference:
-    def __init__(self, model, dtype: str = "float64"):
+    def __init__(self, model, dtype: Optional[str] = None):
+        # dtype None: pgmpy_b200.config, then the application's pgmpy.config when pgmpy is imported, then float64
+        dtype = normalize_dtype(dtype) if dtype is not None else default_dtype()
         self._orig_model = model
         self.model = _as_bn(model)
         if type(self.model).__name__ in ("LinearGaussianBayesianNetwork", "FunctionalBayesianNetwork"):
@@ -53,6 +56,12 @@ class _Inference:
             self.variables = set(self.model.nodes())
         self.cardinality = self.model.get_cardinality()
         self.states = self.model.states
+
+    def _compile(self, plan) -> CompiledPlan:
+        """Upload a plan to the device `config` names (default: the current CUDA device), in this object's dtype."""
+        logger.debug("pgmpy_b200: plan %s, %d steps, %d work entries, dtype %s", plan.meta.get("mode"), plan.n_steps,
+                     plan.ws_entries, self.dtype)
+        return CompiledPlan(plan, self.dtype, device=config.device_index())
 
     # ---- shared checks ---------------------------------------------------------------------
     def _check_query(self, variables, evidence, allow_empty=False):
@@ -155,7 +164,7 @@ class VariableElimination(_Inference):
                     self.model, variables, ev_vars, joint=joint, prune=prune, elimination_order=order_key,
                     reduce_max=reduce_max,
                 )
-            cp = CompiledPlan(plan, self.dtype)
+            cp = self._compile(plan)
             self._plans[key] = cp
         return cp
 
@@ -212,7 +221,7 @@ class VariableElimination(_Inference):
         cp = self._plans.get(key)
         if cp is None:
             plan = PL.compile_ve_multi_plan(self.model, [[v] for v in variables], list(evidence_vars))
-            cp = CompiledPlan(plan, self.dtype)
+            cp = self._compile(plan)
             self._plans[key] = cp
         return cp
 
@@ -293,7 +302,7 @@ class VariableElimination(_Inference):
                 factors = [(tuple(c.variables), c.values, None) for c in self.model.get_cpds()]
             plan = PL.compile_factor_ve_plan(factors, self.cardinality, [nodes[0]], [], joint=True, normalize=False,
                                              reduce_max=True)
-            cp = CompiledPlan(plan, self.dtype)
+            cp = self._compile(plan)
             self._plans[key] = cp
         out = self._run(cp, np.zeros((1, 0), dtype=np.int32))
         return out.max().item()
@@ -377,7 +386,7 @@ class BeliefPropagation(_Inference):
     SURVEY.md §0 fact 5) unless a JunctionTree is passed in, which is then used as given
     (ExactInference.py:742-745)."""
 
-    def __init__(self, model, dtype: str = "float64"):
+    def __init__(self, model, dtype: Optional[str] = None):
         super().__init__(model, dtype)
         if self._unsupported:
             return
@@ -404,7 +413,7 @@ class BeliefPropagation(_Inference):
         cp = self._plans.get(key)
         if cp is None:
             plan = PL.compile_jt_plan(self._jt, ev_vars, variables, emit_beliefs=emit_beliefs)
-            cp = CompiledPlan(plan, self.dtype)
+            cp = self._compile(plan)
             self._plans[key] = cp
         return cp
 
@@ -417,7 +426,7 @@ class BeliefPropagation(_Inference):
         key = ("jt-beliefs", reduce_max)
         cp = self._plans.get(key)
         if cp is None:
-            cp = CompiledPlan(PL.compile_jt_plan(self._jt, [], None, emit_beliefs=True, reduce_max=reduce_max), self.dtype)
+            cp = self._compile(PL.compile_jt_plan(self._jt, [], None, emit_beliefs=True, reduce_max=reduce_max))
             self._plans[key] = cp
         out = self._run(cp, np.zeros((1, 0), dtype=np.int32)).cpu().numpy()[0]
         self.clique_beliefs = {}
@@ -465,7 +474,7 @@ class BeliefPropagation(_Inference):
         if cp is None:
             factors = [(c, p, None) for c, p in zip(self._jt.cliques, self._jt.potentials)]
             plan = PL.compile_factor_ve_plan(factors, self.cardinality, variables, ev_vars, joint=True, normalize=True)
-            cp = CompiledPlan(plan, self.dtype)
+            cp = self._compile(plan)
             self._plans[key] = cp
         out = self._run(cp, states).cpu().numpy()[0]
         self._warn_nan(out)

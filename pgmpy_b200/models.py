@@ -365,7 +365,7 @@ def junction_tree_from_pgmpy(jt) -> JunctionTree:
 
 MODEL_DIR = os.environ.get(
     "PGX_MODEL_DIR",
-    os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "models"),
+    os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "models"),  # package data
 )
 
 
