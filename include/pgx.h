@@ -68,11 +68,8 @@ extern "C" {
 #define PGX_OPT_STEP_KERNEL 5  /* stepwise mode: 0 auto (tile-cooperative kernel, 32-bit addressing) | 1 generic only |
                                   2 tile-cooperative kernel with 64-bit addressing */
 
-#define PGX_OPT_REG_TILE 6     /* stepwise mode: register-tile GEMM-shaped steps (default 0: measured neutral) */
-
-#define PGX_OPT_GEMM_TILE 7    /* stepwise mode: 2-D register-tiled kernel for GEMM-shaped steps (default 0: measured slower) */
-
-#define PGX_OPT_VEC2 8         /* stepwise mode: two evidence sets per lane (16-byte loads) when B >= 64 (default 0) */
+/* options 6, 7, 8 (register-tiled / 2-D register-tiled / two-sets-per-lane variants of the step kernel) were measured
+ * slower than the default on every model (profiles/r01_final_summary.md) and are retired; the numbers stay reserved. */
 
 #define PGX_OPT_STAGE 9        /* stepwise mode: GEMM-shaped two-operand steps run on the TMA-staged register-tile kernel
                                   (pgx_stage.cuh; default 1) */

@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get("PGX_LIB", os.path.join(HERE, "libpgx.so"))  # PGX_LIB
 
 PGX_F64, PGX_F32 = 0, 1
 MODE_AUTO, MODE_STEPWISE, MODE_FUSED = 0, 1, 2
-OPT_MODE, OPT_FUSED_WARPS, OPT_USE_GRAPH, OPT_FUSED_KERNEL, OPT_STEP_KERNEL, OPT_REG_TILE, OPT_GEMM_TILE, OPT_VEC2 = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_MODE, OPT_FUSED_WARPS, OPT_USE_GRAPH, OPT_FUSED_KERNEL, OPT_STEP_KERNEL = 1, 2, 3, 4, 5
 OPT_STAGE = 9
 INFO_N_STEPS, INFO_OUT_ELEMS, INFO_WS_ENTRIES, INFO_LAST_LAUNCHES, INFO_LAST_MODE, INFO_N_EV = 1, 2, 3, 4, 5, 6
 INFO_LAST_VARIANT, INFO_N_LEVELS, INFO_LAST_GRAPH = 7, 8, 9

@@ -44,17 +44,11 @@ int fail(int code, const std::string& msg) {
 
 using namespace pgx;
 
-#ifndef PGX_TILE32V_MINB
-#define PGX_TILE32V_MINB 6  // CTAs per SM for the two-evidence-sets-per-lane tile kernel
-#endif
-#ifndef PGX_TILE32_RT_MINB
-#define PGX_TILE32_RT_MINB 4  // CTAs per SM for the register-tiled instantiation of the 32-bit tile kernel
-#endif
 #ifndef PGX_TILE32_MINB
-#define PGX_TILE32_MINB 8  // same knob for the 32-bit-addressed tile kernel: 32 registers, 64 warps/SM (measured 4..8: 8 is best even with 40 B of spills)
+#define PGX_TILE32_MINB 8  // CTAs per SM for the 32-bit-addressed tile kernel: 32 registers, 64 warps/SM (measured 4..8: 8 is best even with 40 B of spills)
 #endif
 #ifndef PGX_TILE_MINB
-#define PGX_TILE_MINB 5  // CTAs per SM the tile kernel is compiled for (register cap 65536 / (256 * N)); measured 1..6
+#define PGX_TILE_MINB 5  // CTAs per SM the 64-bit tile kernel is compiled for (register cap 65536 / (256 * N)); measured 1..6
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -97,49 +91,20 @@ struct TileItem {
     int32_t blk_begin; // first linear CTA index of this step inside the launch
 };
 
-// K2, tile-cooperative form (the default for steps whose summed range fits the shared offset table).
-// ncu on munin showed the per-thread mixed-radix decomposition costs ~150 issue slots per (entry, warp): SIMT lanes
-// of a warp all decode the SAME entry. Here a CTA owns a tile of `TO` consecutive output entries and up to `btb`
-// tiles of 32 evidence sets:
-//   phase 1  thread t decodes entry tile0 + t ONCE for the whole CTA -> s_otab[t][k]; the summed range is decoded the
-//            same way into s_stab[q][k]  (lanes work on different entries: no redundant index arithmetic);
-//   phase 2  lanes = evidence sets again; a warp streams rows  sum_q prod_k operand_k[(otab + stab) * unit]  with
-//            nothing but shared-memory offset reads, one IMAD.WIDE, the load and the multiply per operand.
-// One launch covers ALL tile-eligible steps of a dependency level (they are independent): the linear CTA index is
-// mapped to its step through `items` (binary search), so the thousands of tiny steps of a large junction tree cost
-// one launch per level instead of one launch each.
-template <typename T, int MAXK, bool RTILE>
-__global__ void __launch_bounds__(256, (RTILE || MAXK > 4) ? 1 : PGX_TILE_MINB) k_contract_tile(const int32_t* __restrict__ pool,
-                                                       const TileItem* __restrict__ items, int n_items, int ev_card_off,
-                                                       const T* __restrict__ cst, const T* __restrict__ ws_in,
-                                                       T* __restrict__ ws_out, const int32_t* __restrict__ ev, int n_ev,
-                                                       int64_t B, int64_t ldb, int bt_log2) {
-    extern __shared__ int32_t s_mem[];
-    // which step does this CTA belong to?
-    int lo = 0, hi = n_items - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (items[mid].blk_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-    }
-    const TileItem it = items[lo];
-    const int local = (int)blockIdx.x - it.blk_begin;
-    const int tile_x = local / it.b_blocks;
-    const int b_block = local - tile_x * it.b_blocks;
-    const int TO = it.TO, btb = it.btb, rec_len = it.rec_len;
-
-    int32_t* s_rec = s_mem;
-    for (int i = threadIdx.x; i < rec_len; i += blockDim.x) s_rec[i] = pool[it.rec_off + i];
-    __syncthreads();
-    const int A = s_rec[0], S = s_rec[1], K = s_rec[2], flags = s_rec[3];
+// Phase 1 of the tile-cooperative kernels: thread t decodes output entry tile0 + t ONCE for the whole CTA into
+// s_otab[t][k] (entry offset of operand k at summed index 0) and the summed range into s_stab[q][k]. Lanes work on
+// different entries, so no lane repeats another's mixed-radix arithmetic (ncu on munin: the per-thread decomposition
+// cost ~150 issue slots per (entry, warp) when every lane decoded the same entry).
+template <int MAXK>
+__device__ __forceinline__ void tile_decode(const int32_t* __restrict__ s_rec, int32_t* __restrict__ s_otab,
+                                            int32_t* __restrict__ s_stab, uint32_t tile0, int TO) {
+    const int A = s_rec[0], S = s_rec[1], K = s_rec[2];
     const int opw = OP_FIXED + A + S;
     const int32_t* odims = s_rec + STEP_FIXED;
     const int32_t* sdims = odims + A;
     const int32_t* ops = sdims + S;
     const uint32_t out_size = (uint32_t)s_rec[4];
     const int sum_size = s_rec[6];
-    int32_t* s_otab = s_mem + ((rec_len + 3) & ~3);
-    int32_t* s_stab = s_otab + TO * K;
-    const uint32_t tile0 = (uint32_t)tile_x * (uint32_t)TO;
     for (int t = threadIdx.x; t < TO; t += blockDim.x) {
         uint32_t rem = tile0 + t;
         int32_t off[MAXK];
@@ -178,6 +143,57 @@ __global__ void __launch_bounds__(256, (RTILE || MAXK > 4) ? 1 : PGX_TILE_MINB) 
         for (int k = 0; k < MAXK; ++k)
             if (k < K) s_stab[qi * K + k] = off[k];
     }
+}
+
+// which step of a level-batched launch does this CTA belong to? (items sorted by blk_begin)
+template <typename Item>
+__device__ __forceinline__ int find_item(const Item* __restrict__ items, int n_items) {
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (items[mid].blk_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// K2, tile-cooperative form (the default for steps whose summed range fits the shared offset table).
+// ncu on munin showed the per-thread mixed-radix decomposition costs ~150 issue slots per (entry, warp): SIMT lanes
+// of a warp all decode the SAME entry. Here a CTA owns a tile of `TO` consecutive output entries and up to `btb`
+// tiles of 32 evidence sets:
+//   phase 1  thread t decodes entry tile0 + t ONCE for the whole CTA -> s_otab[t][k]; the summed range is decoded the
+//            same way into s_stab[q][k]  (lanes work on different entries: no redundant index arithmetic);
+//   phase 2  lanes = evidence sets again; a warp streams rows  sum_q prod_k operand_k[(otab + stab) * unit]  with
+//            nothing but shared-memory offset reads, one IMAD.WIDE, the load and the multiply per operand.
+// One launch covers ALL tile-eligible steps of a dependency level (they are independent): the linear CTA index is
+// mapped to its step through `items` (binary search), so the thousands of tiny steps of a large junction tree cost
+// one launch per level instead of one launch each.
+template <typename T, int MAXK>
+__global__ void __launch_bounds__(256, MAXK > 4 ? 1 : PGX_TILE_MINB) k_contract_tile(const int32_t* __restrict__ pool,
+                                                       const TileItem* __restrict__ items, int n_items, int ev_card_off,
+                                                       const T* __restrict__ cst, const T* __restrict__ ws_in,
+                                                       T* __restrict__ ws_out, const int32_t* __restrict__ ev, int n_ev,
+                                                       int64_t B, int64_t ldb, int bt_log2) {
+    extern __shared__ int32_t s_mem[];
+    const TileItem it = items[find_item(items, n_items)];
+    const int local = (int)blockIdx.x - it.blk_begin;
+    const int tile_x = local / it.b_blocks;
+    const int b_block = local - tile_x * it.b_blocks;
+    const int TO = it.TO, btb = it.btb, rec_len = it.rec_len;
+
+    int32_t* s_rec = s_mem;
+    for (int i = threadIdx.x; i < rec_len; i += blockDim.x) s_rec[i] = pool[it.rec_off + i];
+    __syncthreads();
+    const int A = s_rec[0], S = s_rec[1], K = s_rec[2], flags = s_rec[3];
+    const int opw = OP_FIXED + A + S;
+    const int32_t* odims = s_rec + STEP_FIXED;
+    const int32_t* sdims = odims + A;
+    const int32_t* ops = sdims + S;
+    const uint32_t out_size = (uint32_t)s_rec[4];
+    const int sum_size = s_rec[6];
+    int32_t* s_otab = s_mem + ((rec_len + 3) & ~3);
+    int32_t* s_stab = s_otab + TO * K;
+    const uint32_t tile0 = (uint32_t)tile_x * (uint32_t)TO;
+    tile_decode<MAXK>(s_rec, s_otab, s_stab, tile0, TO);
     __syncthreads();
 
     int n_mul = K;
@@ -253,61 +269,6 @@ __global__ void __launch_bounds__(256, (RTILE || MAXK > 4) ? 1 : PGX_TILE_MINB) 
             }
             continue;
         }
-        if (RTILE && MAXK <= 4 && S > 0 && bt_log2 == 5 && !(flags & (FLAG_DIV | FLAG_MAX)) && TO >= 4) {
-            // GEMM-shaped steps: a thread accumulates RT consecutive output entries at once. An operand whose offset
-            // does not change along that run (it does not contain the fastest output variable) is loaded ONCE per
-            // summed index and reused from a register for all RT outputs, instead of being re-fetched from L1/L2.
-            constexpr int RT = 4;
-            for (int og = warp * RT; og < TO; og += n_warps * RT) {
-                const uint32_t o0 = tile0 + og;
-                if (o0 >= out_size) break;
-                int nr = TO - og < RT ? TO - og : RT;
-                if ((uint32_t)nr > out_size - o0) nr = (int)(out_size - o0);
-                const T* p[RT][MAXK];
-                bool shared[MAXK];
-#pragma unroll
-                for (int k = 0; k < MAXK; ++k) {
-                    shared[k] = true;
-#pragma unroll
-                    for (int r = 0; r < RT; ++r) {
-                        const int rr = r < nr ? r : 0;
-                        const int32_t off = (k < K) ? s_otab[(og + rr) * K + k] : 0;
-                        p[r][k] = base[k] + (int64_t)off * unit[k];
-                        if (p[r][k] != p[0][k]) shared[k] = false;
-                    }
-                }
-                T acc[RT];
-#pragma unroll
-                for (int r = 0; r < RT; ++r) acc[r] = (T)0;
-                const int32_t* st = s_stab;
-#pragma unroll 2
-                for (int q = 0; q < sum_size; ++q, st += K) {
-                    T prod[RT];
-#pragma unroll
-                    for (int r = 0; r < RT; ++r) prod[r] = (T)1;
-#pragma unroll
-                    for (int k = 0; k < MAXK; ++k) {
-                        if (k < K) {
-                            const int64_t so = (int64_t)st[k] * unit[k];
-                            if (shared[k]) {
-                                const T v = p[0][k][so];
-#pragma unroll
-                                for (int r = 0; r < RT; ++r) prod[r] *= v;
-                            } else {
-#pragma unroll
-                                for (int r = 0; r < RT; ++r) prod[r] *= p[r][k][so];
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int r = 0; r < RT; ++r) acc[r] += prod[r];
-                }
-#pragma unroll
-                for (int r = 0; r < RT; ++r)
-                    if (r < nr) out[(int64_t)(o0 + r) * ldb] = acc[r];
-            }
-            continue;
-        }
         for (int og = warp * o_per_warp + o_sub; og < TO; og += og_step) {
             const uint32_t o = tile0 + og;
             if (o >= out_size) break;
@@ -355,20 +316,15 @@ __global__ void __launch_bounds__(256, (RTILE || MAXK > 4) ? 1 : PGX_TILE_MINB) 
 // so an operand element is `wsb[u32 index]` whatever its kind. Per operand the thread keeps two 32-bit values (row
 // base, elements per entry) instead of two 64-bit ones, which brings the kernel to <= 40 registers — the step kernels
 // are latency bound (profiles/r01_diabetes_tile_kernel_ncu.md), so resident warps are what buys throughput.
-template <typename T, int MAXK, bool RTILE>
-__global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ? PGX_TILE32_MINB : 3)) k_contract_tile32(const int32_t* __restrict__ pool,
+template <typename T, int MAXK>
+__global__ void __launch_bounds__(256, MAXK <= 4 ? PGX_TILE32_MINB : 3) k_contract_tile32(const int32_t* __restrict__ pool,
                                                                             const TileItem* __restrict__ items, int n_items,
                                                                             int ev_card_off, const T* __restrict__ ws_in,
                                                                             T* __restrict__ ws_out, uint32_t ws_off0,
                                                                             const int32_t* __restrict__ ev, int n_ev,
                                                                             int64_t B, uint32_t ldb, int bt_log2) {
     extern __shared__ int32_t s_mem[];
-    int lo = 0, hi = n_items - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (items[mid].blk_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-    }
-    const TileItem it = items[lo];
+    const TileItem it = items[find_item(items, n_items)];
     const int local = (int)blockIdx.x - it.blk_begin;
     const int tile_x = local / it.b_blocks;
     const int b_block = local - tile_x * it.b_blocks;
@@ -387,44 +343,7 @@ __global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ?
     int32_t* s_otab = s_mem + ((rec_len + 3) & ~3);
     int32_t* s_stab = s_otab + TO * K;
     const uint32_t tile0 = (uint32_t)tile_x * (uint32_t)TO;
-    for (int t = threadIdx.x; t < TO; t += blockDim.x) {
-        uint32_t rem = tile0 + t;
-        int32_t off[MAXK];
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k) off[k] = 0;
-        if (rem < out_size) {
-            for (int a = A - 1; a >= 0; --a) {
-                const uint32_t d = (uint32_t)odims[a];
-                const uint32_t q = rem / d;
-                const int32_t digit = (int32_t)(rem - q * d);
-                rem = q;
-#pragma unroll
-                for (int k = 0; k < MAXK; ++k)
-                    if (k < K) off[k] += digit * ops[k * opw + OP_FIXED + a];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k)
-            if (k < K) s_otab[t * K + k] = off[k];
-    }
-    for (int qi = threadIdx.x; qi < sum_size; qi += blockDim.x) {
-        uint32_t rem = (uint32_t)qi;
-        int32_t off[MAXK];
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k) off[k] = 0;
-        for (int a = S - 1; a >= 0; --a) {
-            const uint32_t d = (uint32_t)sdims[a];
-            const uint32_t q = rem / d;
-            const int32_t digit = (int32_t)(rem - q * d);
-            rem = q;
-#pragma unroll
-            for (int k = 0; k < MAXK; ++k)
-                if (k < K) off[k] += digit * ops[k * opw + OP_FIXED + A + a];
-        }
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k)
-            if (k < K) s_stab[qi * K + k] = off[k];
-    }
+    tile_decode<MAXK>(s_rec, s_otab, s_stab, tile0, TO);
     __syncthreads();
 
     int n_mul = K;
@@ -492,60 +411,6 @@ __global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ?
             }
             continue;
         }
-        if (RTILE && MAXK <= 4 && S > 0 && bt_log2 == 5 && !(flags & (FLAG_DIV | FLAG_MAX)) && TO >= 4) {
-            // RT consecutive output entries per thread: an operand that does not contain the fastest output variable
-            // has the same row for all of them and is loaded once per summed index (fewer L2->L1 bytes on GEMM-shaped
-            // steps whose small operands are re-read by every output entry)
-            constexpr int RT = 4;
-            for (int og = warp * RT; og < TO; og += n_warps * RT) {
-                const uint32_t o0 = tile0 + og;
-                if (o0 >= out_size) break;
-                int nr = TO - og < RT ? TO - og : RT;
-                if ((uint32_t)nr > out_size - o0) nr = (int)(out_size - o0);
-                uint32_t p[RT][MAXK];
-                bool same[MAXK];
-#pragma unroll
-                for (int k = 0; k < MAXK; ++k) {
-                    same[k] = true;
-#pragma unroll
-                    for (int r = 0; r < RT; ++r) {
-                        const int rr = r < nr ? r : 0;
-                        p[r][k] = (k < K) ? rowb[k] + (uint32_t)s_otab[(og + rr) * K + k] * unit[k] : 0;
-                        if (p[r][k] != p[0][k]) same[k] = false;
-                    }
-                }
-                T acc[RT];
-#pragma unroll
-                for (int r = 0; r < RT; ++r) acc[r] = (T)0;
-                const int32_t* st = s_stab;
-#pragma unroll 2
-                for (int q = 0; q < sum_size; ++q, st += K) {
-                    T prod[RT];
-#pragma unroll
-                    for (int r = 0; r < RT; ++r) prod[r] = (T)1;
-#pragma unroll
-                    for (int k = 0; k < MAXK; ++k) {
-                        if (k < K) {
-                            const uint32_t so = (uint32_t)st[k] * unit[k];
-                            if (same[k]) {
-                                const T v = ws_in[p[0][k] + so];
-#pragma unroll
-                                for (int r = 0; r < RT; ++r) prod[r] *= v;
-                            } else {
-#pragma unroll
-                                for (int r = 0; r < RT; ++r) prod[r] *= ws_in[p[r][k] + so];
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int r = 0; r < RT; ++r) acc[r] += prod[r];
-                }
-#pragma unroll
-                for (int r = 0; r < RT; ++r)
-                    if (r < nr) ws_out[outb + (o0 + r) * ldb] = acc[r];
-            }
-            continue;
-        }
         for (int og = warp * o_per_warp + o_sub; og < TO; og += og_step) {
             const uint32_t o = tile0 + og;
             if (o >= out_size) break;
@@ -584,460 +449,6 @@ __global__ void __launch_bounds__(256, RTILE ? PGX_TILE32_RT_MINB : (MAXK <= 4 ?
                 acc = (r != r) ? (T)0 : r;
             }
             ws_out[outb + o * ldb] = acc;
-        }
-    }
-}
-
-// 16-byte lanes: the same kernel as k_contract_tile32 with TWO evidence sets per lane (b, b+1 — adjacent in the
-// [entry][ldb] layout, so a work-table operand is one 16-byte load and a warp covers 64 evidence sets = a 512-byte row
-// segment). Halves the address arithmetic, offset-table reads and load/store instructions per element and doubles the
-// bytes in flight per warp. Batch-invariant operands are scalar loads: one if the operand has no observed axis, else
-// one per evidence set.
-template <typename T> struct Pair;
-template <> struct Pair<double> { using type = double2; };
-template <> struct Pair<float> { using type = float2; };
-
-template <typename T, int MAXK>
-__global__ void __launch_bounds__(256, MAXK <= 4 ? PGX_TILE32V_MINB : 2) k_contract_tile32v(
-    const int32_t* __restrict__ pool, const TileItem* __restrict__ items, int n_items, int ev_card_off,
-    const T* __restrict__ ws_in, T* __restrict__ ws_out, uint32_t ws_off0, const int32_t* __restrict__ ev, int n_ev, int64_t B,
-    uint32_t ldb) {
-    using V = typename Pair<T>::type;
-    extern __shared__ int32_t s_mem[];
-    int lo = 0, hi = n_items - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (items[mid].blk_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-    }
-    const TileItem it = items[lo];
-    const int local = (int)blockIdx.x - it.blk_begin;
-    const int tile_x = local / it.b_blocks;
-    const int b_block = local - tile_x * it.b_blocks;
-    const int TO = it.TO, btb = it.btb, rec_len = it.rec_len;
-
-    int32_t* s_rec = s_mem;
-    for (int i = threadIdx.x; i < rec_len; i += blockDim.x) s_rec[i] = pool[it.rec_off + i];
-    __syncthreads();
-    const int A = s_rec[0], S = s_rec[1], K = s_rec[2], flags = s_rec[3];
-    const int opw = OP_FIXED + A + S;
-    const int32_t* odims = s_rec + STEP_FIXED;
-    const int32_t* sdims = odims + A;
-    const int32_t* ops = sdims + S;
-    const uint32_t out_size = (uint32_t)s_rec[4];
-    const int sum_size = s_rec[6];
-    int32_t* s_otab = s_mem + ((rec_len + 3) & ~3);
-    int32_t* s_stab = s_otab + TO * K;
-    const uint32_t tile0 = (uint32_t)tile_x * (uint32_t)TO;
-    for (int t = threadIdx.x; t < TO; t += blockDim.x) {
-        uint32_t rem = tile0 + t;
-        int32_t off[MAXK];
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k) off[k] = 0;
-        if (rem < out_size) {
-            for (int a = A - 1; a >= 0; --a) {
-                const uint32_t d = (uint32_t)odims[a];
-                const uint32_t q = rem / d;
-                const int32_t digit = (int32_t)(rem - q * d);
-                rem = q;
-#pragma unroll
-                for (int k = 0; k < MAXK; ++k)
-                    if (k < K) off[k] += digit * ops[k * opw + OP_FIXED + a];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k)
-            if (k < K) s_otab[t * K + k] = off[k];
-    }
-    for (int qi = threadIdx.x; qi < sum_size; qi += blockDim.x) {
-        uint32_t rem = (uint32_t)qi;
-        int32_t off[MAXK];
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k) off[k] = 0;
-        for (int a = S - 1; a >= 0; --a) {
-            const uint32_t d = (uint32_t)sdims[a];
-            const uint32_t q = rem / d;
-            const int32_t digit = (int32_t)(rem - q * d);
-            rem = q;
-#pragma unroll
-            for (int k = 0; k < MAXK; ++k)
-                if (k < K) off[k] += digit * ops[k * opw + OP_FIXED + A + a];
-        }
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k)
-            if (k < K) s_stab[qi * K + k] = off[k];
-    }
-    __syncthreads();
-
-    int n_mul = K;
-    if (flags & FLAG_DIV)
-        while (n_mul > 0 && (ops[(n_mul - 1) * opw] & 0x100)) --n_mul;
-    const bool use_max = (flags & FLAG_MAX) != 0;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const uint32_t out_base = ws_off0 + (uint32_t)s_rec[8] * ldb;
-    const int32_t* ev_card = pool + ev_card_off;
-    // operand classes (warp uniform): bit k of wsm = work table (vector load), bit k of evm = const with observed axes
-    int wsm = 0, evm = 0;
-    for (int k = 0; k < K; ++k) {
-        if ((ops[k * opw] & 0xFF) == 1) wsm |= 1 << k;
-        else if (ops[k * opw + 3] > 0) evm |= 1 << k;
-    }
-    for (int tb = 0; tb < btb; ++tb) {
-        const int64_t b = (((int64_t)b_block * btb + tb) * 32 + lane) * 2;  // this lane owns b and b + 1
-        if (b >= B) continue;                                             // no barriers below
-        const int64_t b1 = b + 1 < B ? b + 1 : b;                         // evidence row of the second set (clamped)
-        uint32_t rowb[MAXK], rowc[MAXK], unit[MAXK];  // rowc: second evidence set's base for const operands
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k) {
-            rowb[k] = 0;
-            rowc[k] = 0;
-            unit[k] = 0;
-            if (k < K) {
-                const int32_t* op = ops + k * opw;
-                uint32_t e = (uint32_t)op[1], e1 = e;
-                const int ne = op[3];
-                if (ne > 0) {
-                    const int32_t* pairs = s_rec + op[4];
-                    for (int j = 0; j < ne; ++j) {
-                        const int slot = pairs[2 * j];
-                        const int32_t card = ev_card[slot];
-                        int32_t st = ev[b * n_ev + slot];
-                        st = st < 0 ? 0 : (st >= card ? card - 1 : st);
-                        e += (uint32_t)(st * pairs[2 * j + 1]);
-                        int32_t s1 = ev[b1 * n_ev + slot];
-                        s1 = s1 < 0 ? 0 : (s1 >= card ? card - 1 : s1);
-                        e1 += (uint32_t)(s1 * pairs[2 * j + 1]);
-                    }
-                }
-                if ((op[0] & 0xFF) == 1) {
-                    unit[k] = ldb;
-                    rowb[k] = ws_off0 + e * ldb + (uint32_t)b;
-                } else {
-                    unit[k] = 1;
-                    rowb[k] = e;
-                    rowc[k] = e1;
-                }
-            }
-        }
-        const uint32_t outb = out_base + (uint32_t)b;
-        for (int og = warp; og < TO; og += n_warps) {
-            const uint32_t o = tile0 + og;
-            if (o >= out_size) break;
-            const int32_t* ot = s_otab + og * K;
-            uint32_t p[MAXK];
-#pragma unroll
-            for (int k = 0; k < MAXK; ++k) p[k] = (k < K) ? (uint32_t)ot[k] * unit[k] : 0;
-            T a0, a1;
-            auto load = [&](int k, uint32_t off, T& x0, T& x1) {
-                if ((wsm >> k) & 1) {
-                    const V v = *reinterpret_cast<const V*>(ws_in + rowb[k] + off);
-                    x0 = v.x;
-                    x1 = v.y;
-                } else {
-                    x0 = ws_in[rowb[k] + off];
-                    x1 = ((evm >> k) & 1) ? ws_in[rowc[k] + off] : x0;
-                }
-            };
-            if (S == 0) {
-                T p0 = (T)1, p1 = (T)1;
-#pragma unroll
-                for (int k = 0; k < MAXK; ++k) {
-                    if (k < n_mul) {
-                        T x0, x1;
-                        load(k, p[k], x0, x1);
-                        p0 *= x0;
-                        p1 *= x1;
-                    }
-                }
-                a0 = p0;
-                a1 = p1;
-            } else {
-                a0 = use_max ? neg_inf<T>() : (T)0;
-                a1 = a0;
-                const int32_t* st = s_stab;
-#pragma unroll 2
-                for (int q = 0; q < sum_size; ++q, st += K) {
-                    T p0 = (T)1, p1 = (T)1;
-#pragma unroll
-                    for (int k = 0; k < MAXK; ++k) {
-                        if (k < n_mul) {
-                            T x0, x1;
-                            load(k, p[k] + (uint32_t)st[k] * unit[k], x0, x1);
-                            p0 *= x0;
-                            p1 *= x1;
-                        }
-                    }
-                    if (use_max) {
-                        a0 = p0 > a0 ? p0 : a0;
-                        a1 = p1 > a1 ? p1 : a1;
-                    } else {
-                        a0 += p0;
-                        a1 += p1;
-                    }
-                }
-            }
-            if (flags & FLAG_DIV) {
-                T d0 = (T)1, d1 = (T)1;
-#pragma unroll
-                for (int k = 0; k < MAXK; ++k) {
-                    if (k >= n_mul && k < K) {
-                        T x0, x1;
-                        load(k, p[k], x0, x1);
-                        d0 *= x0;
-                        d1 *= x1;
-                    }
-                }
-                const T r0 = a0 / d0, r1 = a1 / d1;
-                a0 = (r0 != r0) ? (T)0 : r0;
-                a1 = (r1 != r1) ? (T)0 : r1;
-            }
-            V res;
-            res.x = a0;
-            res.y = a1;
-            *reinterpret_cast<V*>(ws_out + outb + o * ldb) = res;
-        }
-    }
-}
-
-// K3 — GEMM-shaped steps (two or three operands sharing the summed variables, each depending on only part of the
-// output scope; diabetes, parts of pathfinder/munin). Same launch contract and phase 1 as k_contract_tile32; in phase 2
-// a thread owns an R2 x R1 block of the output seen as a matrix [slower axes][fastest axis] and keeps R2*R1
-// accumulators in registers. Inside such a block an operand's entry offset is separable,
-//     e(r2, r1) = e00 + d2[r2] + d1[r1],
-// and an operand that does not contain the fastest output variable has d1 == 0 (one row per r2 serves R1 outputs),
-// one that does not contain the next-slower variable has d2 == 0. Per summed index the thread therefore loads
-// R2 + R1 rows of the two small operands instead of 2*R2*R1 — the reuse a GEMM tile gets from registers — which cuts
-// the L2->L1 re-reads that bound these steps. fp64 has no tcgen05 kind and DMMA peaks where DFMA does on B200, and the
-// fp64 pipe is < 10 % busy here, so the tile is fed by plain DFMA.
-template <typename T, int MAXK>
-__global__ void __launch_bounds__(256, 3) k_contract_gemm32(const int32_t* __restrict__ pool,
-                                                            const TileItem* __restrict__ items, int n_items,
-                                                            int ev_card_off, const T* __restrict__ ws_in,
-                                                            T* __restrict__ ws_out, uint32_t ws_off0,
-                                                            const int32_t* __restrict__ ev, int n_ev, int64_t B,
-                                                            uint32_t ldb) {
-    constexpr int R1 = 3, R2 = 3;
-    extern __shared__ int32_t s_mem[];
-    int lo = 0, hi = n_items - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (items[mid].blk_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-    }
-    const TileItem it = items[lo];
-    const int local = (int)blockIdx.x - it.blk_begin;
-    const int tile_x = local / it.b_blocks;
-    const int b_block = local - tile_x * it.b_blocks;
-    const int TO = it.TO, btb = it.btb, rec_len = it.rec_len;
-
-    int32_t* s_rec = s_mem;
-    for (int i = threadIdx.x; i < rec_len; i += blockDim.x) s_rec[i] = pool[it.rec_off + i];
-    __syncthreads();
-    const int A = s_rec[0], S = s_rec[1], K = s_rec[2];
-    const int opw = OP_FIXED + A + S;
-    const int32_t* odims = s_rec + STEP_FIXED;
-    const int32_t* sdims = odims + A;
-    const int32_t* ops = sdims + S;
-    const uint32_t out_size = (uint32_t)s_rec[4];
-    const int sum_size = s_rec[6];
-    int32_t* s_otab = s_mem + ((rec_len + 3) & ~3);
-    int32_t* s_stab = s_otab + TO * K;
-    const uint32_t tile0 = (uint32_t)tile_x * (uint32_t)TO;
-    for (int t = threadIdx.x; t < TO; t += blockDim.x) {
-        uint32_t rem = tile0 + t;
-        int32_t off[MAXK];
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k) off[k] = 0;
-        if (rem < out_size) {
-            for (int a = A - 1; a >= 0; --a) {
-                const uint32_t d = (uint32_t)odims[a];
-                const uint32_t q = rem / d;
-                const int32_t digit = (int32_t)(rem - q * d);
-                rem = q;
-#pragma unroll
-                for (int k = 0; k < MAXK; ++k)
-                    if (k < K) off[k] += digit * ops[k * opw + OP_FIXED + a];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k)
-            if (k < K) s_otab[t * K + k] = off[k];
-    }
-    for (int qi = threadIdx.x; qi < sum_size; qi += blockDim.x) {
-        uint32_t rem = (uint32_t)qi;
-        int32_t off[MAXK];
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k) off[k] = 0;
-        for (int a = S - 1; a >= 0; --a) {
-            const uint32_t d = (uint32_t)sdims[a];
-            const uint32_t q = rem / d;
-            const int32_t digit = (int32_t)(rem - q * d);
-            rem = q;
-#pragma unroll
-            for (int k = 0; k < MAXK; ++k)
-                if (k < K) off[k] += digit * ops[k * opw + OP_FIXED + A + a];
-        }
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k)
-            if (k < K) s_stab[qi * K + k] = off[k];
-    }
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const int n1 = odims[A - 1];                 // fastest output axis (host guarantees A >= 1 and TO % n1 == 0)
-    const int rows_in_tile = TO / n1;
-    const int col_blocks = (n1 + R1 - 1) / R1;
-    const int row_blocks = (rows_in_tile + R2 - 1) / R2;
-    const uint32_t out_base = ws_off0 + (uint32_t)s_rec[8] * ldb;
-    const int32_t* ev_card = pool + ev_card_off;
-    for (int tb = 0; tb < btb; ++tb) {
-        const int64_t b = ((int64_t)b_block * btb + tb) * 32 + lane;
-        if (b >= B) continue;  // no barriers below
-        uint32_t rowb[MAXK], unit[MAXK];
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k) {
-            rowb[k] = 0;
-            unit[k] = 0;
-            if (k < K) {
-                const int32_t* op = ops + k * opw;
-                uint32_t e = (uint32_t)op[1];
-                const int ne = op[3];
-                if (ne > 0) {
-                    const int32_t* pairs = s_rec + op[4];
-                    for (int j = 0; j < ne; ++j) {
-                        const int slot = pairs[2 * j];
-                        int32_t st = ev[b * n_ev + slot];
-                        const int32_t card = ev_card[slot];
-                        st = st < 0 ? 0 : (st >= card ? card - 1 : st);
-                        e += (uint32_t)(st * pairs[2 * j + 1]);
-                    }
-                }
-                if ((op[0] & 0xFF) == 1) {
-                    unit[k] = ldb;
-                    rowb[k] = ws_off0 + e * ldb + (uint32_t)b;
-                } else {
-                    unit[k] = 1;
-                    rowb[k] = e;
-                }
-            }
-        }
-        const uint32_t outb = out_base + (uint32_t)b;
-        for (int blk = warp; blk < row_blocks * col_blocks; blk += n_warps) {
-            const int rb = blk / col_blocks, cb = blk - rb * col_blocks;
-            const int r0 = rb * R2, c0 = cb * R1;
-            const uint32_t o00 = tile0 + (uint32_t)(r0 * n1 + c0);
-            if (o00 >= out_size) continue;
-            int nr2 = rows_in_tile - r0 < R2 ? rows_in_tile - r0 : R2;
-            const int rows_left = (int)((out_size - (tile0 + (uint32_t)(r0 * n1))) / (uint32_t)n1);
-            if (nr2 > rows_left) nr2 = rows_left;
-            const int nc = n1 - c0 < R1 ? n1 - c0 : R1;
-            // separable offsets of every operand inside the block (checked: any deviation -> entry-by-entry path)
-            uint32_t e00[MAXK], d1[MAXK][R1], d2[MAXK][R2];
-            bool separable = true;
-#pragma unroll
-            for (int k = 0; k < MAXK; ++k) {
-                e00[k] = 0;
-#pragma unroll
-                for (int r = 0; r < R1; ++r) d1[k][r] = 0;
-#pragma unroll
-                for (int r = 0; r < R2; ++r) d2[k][r] = 0;
-                if (k < K) {
-                    const int32_t base = s_otab[(r0 * n1 + c0) * K + k];
-                    e00[k] = rowb[k] + (uint32_t)base * unit[k];
-#pragma unroll
-                    for (int r = 1; r < R1; ++r)
-                        if (r < nc) d1[k][r] = (uint32_t)(s_otab[(r0 * n1 + c0 + r) * K + k] - base) * unit[k];
-#pragma unroll
-                    for (int r = 1; r < R2; ++r)
-                        if (r < nr2) d2[k][r] = (uint32_t)(s_otab[((r0 + r) * n1 + c0) * K + k] - base) * unit[k];
-#pragma unroll
-                    for (int r2 = 1; r2 < R2; ++r2)
-#pragma unroll
-                        for (int r1 = 1; r1 < R1; ++r1)
-                            if (r2 < nr2 && r1 < nc &&
-                                (uint32_t)(s_otab[((r0 + r2) * n1 + c0 + r1) * K + k] - base) * unit[k] != d1[k][r1] + d2[k][r2])
-                                separable = false;
-                }
-            }
-            if (!separable) {
-                for (int r2 = 0; r2 < nr2; ++r2)
-                    for (int r1 = 0; r1 < nc; ++r1) {
-                        const int og = (r0 + r2) * n1 + c0 + r1;
-                        T acc = (T)0;
-                        const int32_t* st = s_stab;
-                        for (int q = 0; q < sum_size; ++q, st += K) {
-                            T prod = (T)1;
-#pragma unroll
-                            for (int k = 0; k < MAXK; ++k)
-                                if (k < K) prod *= ws_in[rowb[k] + (uint32_t)(s_otab[og * K + k] + st[k]) * unit[k]];
-                            acc += prod;
-                        }
-                        ws_out[outb + (tile0 + (uint32_t)og) * ldb] = acc;
-                    }
-                continue;
-            }
-            bool dep1[MAXK], dep2[MAXK];
-#pragma unroll
-            for (int k = 0; k < MAXK; ++k) {
-                dep1[k] = false;
-                dep2[k] = false;
-#pragma unroll
-                for (int r = 1; r < R1; ++r) dep1[k] = dep1[k] || d1[k][r] != 0;
-#pragma unroll
-                for (int r = 1; r < R2; ++r) dep2[k] = dep2[k] || d2[k][r] != 0;
-            }
-            T acc[R2][R1];
-#pragma unroll
-            for (int r2 = 0; r2 < R2; ++r2)
-#pragma unroll
-                for (int r1 = 0; r1 < R1; ++r1) acc[r2][r1] = (T)0;
-            const int32_t* st = s_stab;
-            for (int q = 0; q < sum_size; ++q, st += K) {
-                T prod[R2][R1];
-#pragma unroll
-                for (int r2 = 0; r2 < R2; ++r2)
-#pragma unroll
-                    for (int r1 = 0; r1 < R1; ++r1) prod[r2][r1] = (T)1;
-#pragma unroll
-                for (int k = 0; k < MAXK; ++k) {
-                    if (k < K) {
-                        const uint32_t a0 = e00[k] + (uint32_t)st[k] * unit[k];
-                        if (dep1[k] && dep2[k]) {
-#pragma unroll
-                            for (int r2 = 0; r2 < R2; ++r2)
-#pragma unroll
-                                for (int r1 = 0; r1 < R1; ++r1) prod[r2][r1] *= ws_in[a0 + d2[k][r2] + d1[k][r1]];
-                        } else if (dep2[k]) {
-#pragma unroll
-                            for (int r2 = 0; r2 < R2; ++r2) {
-                                const T v = ws_in[a0 + d2[k][r2]];
-#pragma unroll
-                                for (int r1 = 0; r1 < R1; ++r1) prod[r2][r1] *= v;
-                            }
-                        } else if (dep1[k]) {
-#pragma unroll
-                            for (int r1 = 0; r1 < R1; ++r1) {
-                                const T v = ws_in[a0 + d1[k][r1]];
-#pragma unroll
-                                for (int r2 = 0; r2 < R2; ++r2) prod[r2][r1] *= v;
-                            }
-                        } else {
-                            const T v = ws_in[a0];
-#pragma unroll
-                            for (int r2 = 0; r2 < R2; ++r2)
-#pragma unroll
-                                for (int r1 = 0; r1 < R1; ++r1) prod[r2][r1] *= v;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int r2 = 0; r2 < R2; ++r2)
-#pragma unroll
-                    for (int r1 = 0; r1 < R1; ++r1) acc[r2][r1] += prod[r2][r1];
-            }
-#pragma unroll
-            for (int r2 = 0; r2 < R2; ++r2)
-#pragma unroll
-                for (int r1 = 0; r1 < R1; ++r1)
-                    if (r2 < nr2 && r1 < nc) ws_out[outb + (o00 + (uint32_t)(r2 * n1 + r1)) * ldb] = acc[r2][r1];
         }
     }
 }
@@ -1178,8 +589,6 @@ struct LaunchGroup {
     int generic_step = -1;  // >= 0: one launch of the generic kernel for this step
     int first_item = 0, n_items = 0, n_blocks = 0, max_k = 0;
     size_t smem = 0;
-    bool rtile = false;  // the group holds GEMM-shaped steps: use the register-tiled instantiation
-    bool gemm = false;   // every step of the group goes to k_contract_gemm32 (2-D register tile)
     bool stage = false;  // every step of the group goes to k_contract_stage (TMA-staged GEMM tiles)
     std::vector<int> step_ids;  // plan steps served by this launch (tracing: pgx_profile_launches)
 };
@@ -1290,7 +699,6 @@ static bool pick_stage(const int32_t* r, int64_t out_size, int64_t sum_size, siz
 struct StepSchedule {
     int64_t B = 0;
     int step_kernel = 0, dtype_size = 0;
-    bool vec2 = false;  // tile groups use the two-evidence-sets-per-lane kernel (64 evidence sets per warp)
     std::vector<LaunchGroup> groups;
     TileItem* d_items = nullptr;
     pgx::StageItem* d_stage_items = nullptr;
@@ -1329,9 +737,6 @@ struct pgx_plan {
     std::vector<StepSchedule> schedules;
     cudaStream_t cap_stream = nullptr;
     int last_graph = 0;
-    int vec2 = 0;         // tile kernel with two evidence sets per lane when B >= 64 (PGX_OPT_VEC2); measured slower, opt-in
-    int gemm_tile = 0;    // route GEMM-shaped steps to k_contract_gemm32 (PGX_OPT_GEMM_TILE); measured slower, opt-in
-    int reg_tile = 0;     // register-tile GEMM-shaped steps (PGX_OPT_REG_TILE); measured neutral-to-slower, off by default
     int stage = 1;        // GEMM-shaped two-operand steps go to the TMA-staged register-tile kernel (PGX_OPT_STAGE)
     int batch_levels = 1; // share one launch among the tile-eligible steps of a dependency level
     cudaEvent_t* prof_events = nullptr;  // set only inside pgx_profile_steps
@@ -1536,14 +941,8 @@ int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
         case PGX_OPT_USE_GRAPH:
             plan->use_graph = value ? 1 : 0;
             return PGX_OK;
-        case PGX_OPT_VEC2:
-        case PGX_OPT_GEMM_TILE:
-        case PGX_OPT_REG_TILE:
         case PGX_OPT_STAGE:
-            if (option == PGX_OPT_STAGE) plan->stage = value ? 1 : 0;
-            else if (option == PGX_OPT_GEMM_TILE) plan->gemm_tile = value ? 1 : 0;
-            else if (option == PGX_OPT_VEC2) plan->vec2 = value ? 1 : 0;
-            else plan->reg_tile = value ? 1 : 0;
+            plan->stage = value ? 1 : 0;
             for (StepSchedule& c : plan->schedules) {
                 if (c.d_items) cudaFree(c.d_items);
                 if (c.d_stage_items) cudaFree(c.d_stage_items);
@@ -1683,42 +1082,37 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
         // launch schedule for this batch size: tile-eligible steps of one dependency level share a launch
         StepSchedule* sched = nullptr;
         for (StepSchedule& c : pl->schedules)
-            if (c.B == B && c.step_kernel == pl->step_kernel + 4 * pl->batch_levels + 8 * pl->gemm_tile + 16 * pl->vec2 + 32 * pl->stage &&
+            if (c.B == B && c.step_kernel == pl->step_kernel + 4 * pl->batch_levels + 32 * pl->stage &&
                 c.dtype_size == (int)sizeof(T))
                 sched = &c;
         if (!sched) {
             StepSchedule ns;
             ns.B = B;
-            ns.step_kernel = pl->step_kernel + 4 * pl->batch_levels + 8 * pl->gemm_tile + 16 * pl->vec2 + 32 * pl->stage;
-            // 16-byte lanes when the batch is wide enough and 32-bit addressing applies (checked again at launch)
-            ns.vec2 = pl->vec2 && pl->step_kernel == 0 && bt_log2 == 5 && B >= 64 && !pl->gemm_tile && !pl->reg_tile &&
-                      ws_off0 + (size_t)pl->ws_entries * (size_t)ldb < (1ULL << 32) && pl->ws_entries < (1LL << 31);
-            const int64_t tile_b_tiles = ns.vec2 ? (B + 63) / 64 : b_tiles;
+            ns.step_kernel = pl->step_kernel + 4 * pl->batch_levels + 32 * pl->stage;
+            const int64_t tile_b_tiles = b_tiles;
             ns.dtype_size = (int)sizeof(T);
             std::vector<TileItem> items;
             const int o_per_warp = 32 >> bt_log2;
-            std::vector<TileItem> pending[2];  // items of the open plain / GEMM-shaped group of the current level
+            std::vector<TileItem> pending;  // items of the open tile group of the current level
             auto flush = [&](LaunchGroup& g) {
                 if (g.n_items > 0) {
-                    std::vector<TileItem>& pv = pending[g.gemm ? 1 : 0];
                     g.first_item = (int)items.size();
-                    items.insert(items.end(), pv.begin(), pv.end());
-                    pv.clear();
+                    items.insert(items.end(), pending.begin(), pending.end());
+                    pending.clear();
                     ns.groups.push_back(g);
                 }
                 g = LaunchGroup();
             };
-            // per dependency level: one group of plain tile steps, one group of GEMM-shaped steps, generic steps alone
-            LaunchGroup cur[2];
+            // per dependency level: one group of tile steps, generic steps alone
+            LaunchGroup cur;
             // ... and one group of steps for the TMA-staged GEMM-tile kernel
             LaunchGroup cur_stage;
             std::vector<StageItem> stage_items, pending_stage;
-            const bool stage_on = pl->stage && pl->step_kernel == 0 && bt_log2 == 5 && !ns.vec2 &&
+            const bool stage_on = pl->stage && pl->step_kernel == 0 && bt_log2 == 5 &&
                                   ws_off0 + (size_t)pl->ws_entries * (size_t)ldb < (1ULL << 32) && pl->ws_entries < (1LL << 31);
             int cur_level = -1;
             auto flush_level = [&]() {
-                flush(cur[0]);
-                flush(cur[1]);
+                flush(cur);
                 if (cur_stage.n_items > 0) {
                     cur_stage.first_item = (int)stage_items.size();
                     stage_items.insert(stage_items.end(), pending_stage.begin(), pending_stage.end());
@@ -1731,14 +1125,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                 const StepInfo& s = pl->steps[si];
                 const int64_t stab_words = s.sum_size * s.n_ops;
                 const bool tile_ok = s.n_ops <= 8 && stab_words <= 8192 && pl->step_kernel != 1;  // 0 tile32, 2 tile64
-                // GEMM-shaped: a summed range worth tiling, 2..4 plain operands, a fastest output axis of >= 2 entries
-                // and at least 3 rows of it; such steps form their own launch groups (k_contract_gemm32)
                 const int32_t* srec = pl->pool.data() + s.rec_off;
-                const int sA = srec[0];
-                const int n1 = sA > 0 ? srec[STEP_FIXED + sA - 1] : 1;
-                const bool gemm_ok = tile_ok && pl->gemm_tile && pl->step_kernel == 0 && bt_log2 == 5 && srec[3] == 0 &&
-                                     s.n_ops >= 2 && s.n_ops <= 4 && s.sum_size >= 8 && sA >= 2 && n1 >= 2 && n1 <= 128 &&
-                                     s.out_size / n1 >= 3 && s.out_size * s.sum_size >= 4096;
                 if (s.level != cur_level || !pl->batch_levels) flush_level();
                 cur_level = s.level;
                 if (stage_on && tile_ok) {
@@ -1769,7 +1156,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                     ns.groups.push_back(g);
                     continue;
                 }
-                int btb = (int)(tile_b_tiles < 4 ? tile_b_tiles : (ns.vec2 ? 2 : 4));
+                int btb = (int)(tile_b_tiles < 4 ? tile_b_tiles : 4);
                 int64_t b_blocks = (tile_b_tiles + btb - 1) / btb;
                 int64_t TO = (s.out_size * b_blocks) / (148 * 4);  // aim at >= 4 CTAs per SM when there is work
                 if (TO < 8 * o_per_warp) {
@@ -1782,22 +1169,14 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                 if (TO * s.n_ops > 2048) TO = 2048 / s.n_ops;
                 TO = (TO + o_per_warp - 1) / o_per_warp * o_per_warp;
                 if (TO > s.out_size) TO = (s.out_size + o_per_warp - 1) / o_per_warp * o_per_warp;
-                if (gemm_ok) {
-                    // whole rows of the fastest axis, a multiple of 3 of them
-                    int64_t rows = std::max<int64_t>(3, (TO / n1) / 3 * 3);
-                    while (rows > 3 && rows * n1 * s.n_ops > 2048) rows -= 3;
-                    TO = rows * n1;
-                }
-                LaunchGroup& cg = cur[gemm_ok ? 1 : 0];
+                LaunchGroup& cg = cur;
                 const int64_t n_blocks = ((s.out_size + TO - 1) / TO) * b_blocks;
                 if (cg.n_items > 0 && (int64_t)cg.n_blocks + n_blocks > (1LL << 30)) flush(cg);
-                pending[gemm_ok ? 1 : 0].push_back(TileItem{s.rec_off, s.rec_len, (int32_t)TO, btb, (int32_t)b_blocks, (int32_t)cg.n_blocks});
-                cg.gemm = gemm_ok;
+                pending.push_back(TileItem{s.rec_off, s.rec_len, (int32_t)TO, btb, (int32_t)b_blocks, (int32_t)cg.n_blocks});
                 cg.step_ids.push_back((int)si);
                 cg.n_items += 1;
                 cg.n_blocks += (int)n_blocks;
                 cg.max_k = std::max(cg.max_k, s.n_ops);
-                if (s.sum_size >= 4 && s.n_ops >= 2 && s.out_size >= 64) cg.rtile = true;
                 cg.smem = std::max(cg.smem, (size_t)(((s.rec_len + 3) & ~3) + TO * s.n_ops + stab_words) * sizeof(int32_t));
             }
             flush_level();
@@ -1857,51 +1236,25 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                                                                                   (uint32_t)ldb);
                 } else {
                     const TileItem* d_it = sched->d_items + g.first_item;
-#define PGX_LAUNCH_TILE(MK, RT)                                                                                            \
-    k_contract_tile<T, MK, RT><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off, cst, \
-                                                                          ws, ws, ev, pl->n_ev, B, ldb, bt_log2)
-                    const bool rt = g.rtile && pl->reg_tile && bt_log2 == 5;
-                    if (idx32 && sched->vec2) {
-#define PGX_LAUNCH_TILE32V(MK)                                                                                              \
-    k_contract_tile32v<T, MK><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off, ws_all, \
-                                                                         ws_all, (uint32_t)ws_off0, ev, pl->n_ev, B,          \
-                                                                         (uint32_t)ldb)
-                        if (g.max_k <= 2)
-                            PGX_LAUNCH_TILE32V(2);
-                        else if (g.max_k <= 4)
-                            PGX_LAUNCH_TILE32V(4);
-                        else
-                            PGX_LAUNCH_TILE32V(8);
-#undef PGX_LAUNCH_TILE32V
-                    } else if (idx32 && g.gemm) {
-                        if (g.max_k <= 2)
-                            k_contract_gemm32<T, 2><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(
-                                pl->d_pool, d_it, g.n_items, pl->ev_card_off, ws_all, ws_all, (uint32_t)ws_off0, ev, pl->n_ev, B,
-                                (uint32_t)ldb);
-                        else
-                            k_contract_gemm32<T, 4><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(
-                                pl->d_pool, d_it, g.n_items, pl->ev_card_off, ws_all, ws_all, (uint32_t)ws_off0, ev, pl->n_ev, B,
-                                (uint32_t)ldb);
-                    } else if (idx32) {
-#define PGX_LAUNCH_TILE32(MK, RT)                                                                                          \
-    k_contract_tile32<T, MK, RT><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off,   \
-                                                                            ws_all, ws_all, (uint32_t)ws_off0, ev, pl->n_ev, \
-                                                                            B, (uint32_t)ldb, bt_log2)
-                        if (g.max_k <= 2) {
-                            if (rt) PGX_LAUNCH_TILE32(2, true); else PGX_LAUNCH_TILE32(2, false);
-                        } else if (g.max_k <= 4) {
-                            if (rt) PGX_LAUNCH_TILE32(4, true); else PGX_LAUNCH_TILE32(4, false);
-                        } else {
-                            PGX_LAUNCH_TILE32(8, false);
-                        }
-#undef PGX_LAUNCH_TILE32
+#define PGX_LAUNCH_TILE(MK)                                                                                            \
+    k_contract_tile<T, MK><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off, cst, \
+                                                                      ws, ws, ev, pl->n_ev, B, ldb, bt_log2)
+#define PGX_LAUNCH_TILE32(MK)                                                                                          \
+    k_contract_tile32<T, MK><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, d_it, g.n_items, pl->ev_card_off,   \
+                                                                        ws_all, ws_all, (uint32_t)ws_off0, ev, pl->n_ev, \
+                                                                        B, (uint32_t)ldb, bt_log2)
+                    if (idx32) {
+                        if (g.max_k <= 2) PGX_LAUNCH_TILE32(2);
+                        else if (g.max_k <= 4) PGX_LAUNCH_TILE32(4);
+                        else PGX_LAUNCH_TILE32(8);
                     } else if (g.max_k <= 2) {
-                        if (rt) PGX_LAUNCH_TILE(2, true); else PGX_LAUNCH_TILE(2, false);
+                        PGX_LAUNCH_TILE(2);
                     } else if (g.max_k <= 4) {
-                        if (rt) PGX_LAUNCH_TILE(4, true); else PGX_LAUNCH_TILE(4, false);
+                        PGX_LAUNCH_TILE(4);
                     } else {
-                        PGX_LAUNCH_TILE(8, false);
+                        PGX_LAUNCH_TILE(8);
                     }
+#undef PGX_LAUNCH_TILE32
 #undef PGX_LAUNCH_TILE
                 }
                 ++n;

@@ -93,15 +93,6 @@ class CompiledPlan:
         v = self.info(N.INFO_LAST_VARIANT)
         return {0: "stepwise", 1: "generic", 2: "tables-smem", 3: "tables-global"}[v]
 
-    def set_vec2(self, enabled: bool = True):
-        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_VEC2, 1 if enabled else 0))
-
-    def set_gemm_tile(self, enabled: bool = True):
-        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_GEMM_TILE, 1 if enabled else 0))
-
-    def set_reg_tile(self, enabled: bool = True):
-        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_REG_TILE, 1 if enabled else 0))
-
     def set_stage(self, enabled: bool = True):
         """GEMM-shaped two-operand steps on the TMA-staged register-tile kernel (default on)."""
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_STAGE, 1 if enabled else 0))

@@ -572,24 +572,6 @@ def test_predict_and_predict_probability(torch_cuda):
         m.predict_probability(data.assign(bogus=1))
 
 
-def test_register_tiled_steps_match(torch_cuda):
-    """GEMM-shaped steps through the register-tiled instantiation of k_contract_tile == the plain one."""
-    torch = torch_cuda
-    m = px.get_example_model("diabetes")
-    ev_vars, states = sample_evidence(m, 64, 8, seed=3)
-    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars)
-    cp = _engine()(plan)
-    cp.set_mode("stepwise")
-    ev = torch.from_numpy(states).cuda()
-    cp.set_reg_tile(False)
-    plain = cp.run(ev).clone()
-    cp.set_reg_tile(True)
-    tiled = cp.run(ev)
-    assert float(((tiled - plain).abs() / plain.abs().clamp_min(1e-300)).max()) <= 1e-13
-    want = run_plan(plan.pool, plan.const_blob, states[:4])
-    assert rel_err(tiled[:4].cpu().numpy(), want) <= 1e-12
-
-
 def test_edge_cases_tiny_networks_and_no_evidence(torch_cuda):
     """Degenerate shapes: a single-node network, a two-node chain, queries without evidence, every variable but one
     observed, scalar (empty-sepset) messages in a disconnected network."""
@@ -688,47 +670,6 @@ def test_bp_on_user_junction_tree_calibrate_and_max_calibrate(torch_cuda):
                              O.Factor(["C", "D"], np.arange(4.0).reshape(2, 2)))
     want = O.normalize(O.marginalize(O.reduce(joint, [("D", 1)]), ["B", "C"]))
     np.testing.assert_allclose(q.values, want.values, rtol=1e-13)
-
-
-@pytest.mark.parametrize("name", ["diabetes", "pathfinder", "hepar2"])
-def test_gemm_shaped_step_kernel_matches(torch_cuda, name):
-    """k_contract_gemm32 (2-D register tile for GEMM-shaped steps) vs the plain tile kernel and the oracle."""
-    torch = torch_cuda
-    m = px.get_example_model(name)
-    B = 70  # three tiles of 32 evidence sets, the last one ragged
-    ev_vars, states = sample_evidence(m, B, 8, seed=13)
-    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars)
-    cp = _engine()(plan)
-    cp.set_mode("stepwise")
-    ev = torch.from_numpy(states).cuda()
-    cp.set_gemm_tile(False)
-    plain = cp.run(ev).clone()
-    cp.set_gemm_tile(True)
-    tiled = cp.run(ev)
-    assert float(((tiled - plain).abs() / plain.abs().clamp_min(1e-300)).max()) <= 1e-13
-    want = run_plan(plan.pool, plan.const_blob, states[:3])
-    assert rel_err(tiled[:3].cpu().numpy(), want) <= 1e-12
-
-
-@pytest.mark.parametrize("name,B", [("hepar2", 64), ("hepar2", 333), ("pathfinder", 97), ("diabetes", 70)])
-def test_two_sets_per_lane_tile_kernel_matches(torch_cuda, name, B):
-    """k_contract_tile32v (16-byte lanes: evidence sets b and b+1 per lane) vs the scalar-lane kernel and the oracle,
-    including odd batch sizes where the last lane's second set is padding."""
-    torch = torch_cuda
-    m = px.get_example_model(name)
-    ev_vars, states = sample_evidence(m, B, 8, seed=17)
-    for distribute in ("auto", "divide"):
-        plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, distribute=distribute)
-        cp = _engine()(plan)
-        cp.set_mode("stepwise")
-        ev = torch.from_numpy(states).cuda()
-        cp.set_vec2(False)
-        scalar = cp.run(ev).clone()
-        cp.set_vec2(True)
-        vec = cp.run(ev)
-        assert torch.equal(vec, scalar)
-        want = run_plan(plan.pool, plan.const_blob, states[-3:])
-        assert rel_err(vec[-3:].cpu().numpy(), want) <= 1e-12
 
 
 def test_engine_argument_errors(torch_cuda):

@@ -122,7 +122,7 @@ def mixed_ve(name, batch=262144, n_sig=16):
                       "alg_GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / PEAK}), flush=True)
 
 
-def bp_all_marginals(name, batch, k=8, reps=3, reg_tile=False):
+def bp_all_marginals(name, batch, k=8, reps=3):
     """configs[3]/[4]: large-table junction-tree all-marginals (pathfinder, diabetes, munin)."""
     m = px.get_example_model(name)
     bp = BeliefPropagation(m)
@@ -130,13 +130,12 @@ def bp_all_marginals(name, batch, k=8, reps=3, reg_tile=False):
     t0 = time.perf_counter()
     cp = bp.marginals_plan(ev_vars)
     compile_s = time.perf_counter() - t0
-    cp.set_reg_tile(reg_tile)
     ev = torch.from_numpy(states).cuda()
     out = torch.empty((batch, cp.out_elems), dtype=torch.float64, device="cuda")
     ms = timed(lambda: cp.run(ev, out=out), warm=2, reps=reps)
     alg = cp.plan.algorithmic_bytes(batch)
     print(json.dumps({"config": f"{name} junction-tree all-variable marginals", "batch": batch, "mode": cp.last_mode, "variant": cp.last_variant,
-                      "launches": cp.last_launches, "steps": cp.plan.n_steps, "reg_tile": reg_tile, "plan_compile_s": round(compile_s, 2), "ms_per_batch": ms,
+                      "launches": cp.last_launches, "steps": cp.plan.n_steps, "plan_compile_s": round(compile_s, 2), "ms_per_batch": ms,
                       "evidence_queries_per_sec": batch / ms * 1e3, "alg_bytes_per_evidence_set": alg / batch,
                       "alg_GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / PEAK,
                       "workspace_GB": cp.workspace_bytes(batch) / 1e9}), flush=True)
@@ -156,13 +155,8 @@ if __name__ == "__main__":
         bp_all_marginals("pathfinder", 16384)
         bp_all_marginals("diabetes", 2048)
     if what and what[0] == "one":
-        bp_all_marginals(what[1], int(what[2]), reps=int(what[3]) if len(what) > 3 else 3,
-                         reg_tile=bool(int(what[4])) if len(what) > 4 else False)
+        bp_all_marginals(what[1], int(what[2]), reps=int(what[3]) if len(what) > 3 else 3)
         sys.exit(0)
-    if "rtile" in what:
-        for name, b in (("pathfinder", 4096), ("diabetes", 1024), ("munin", 64)):
-            for rt in (False, True):
-                bp_all_marginals(name, b, reg_tile=rt)
     if "munin" in what:
         for b in (64, 256, 1024):
             bp_all_marginals("munin", b)
