@@ -71,8 +71,11 @@ extern "C" {
 /* options 6, 7, 8 (register-tiled / 2-D register-tiled / two-sets-per-lane variants of the step kernel) were measured
  * slower than the default on every model (profiles/r01_final_summary.md) and are retired; the numbers stay reserved. */
 
-#define PGX_OPT_STAGE 9        /* stepwise mode: GEMM-shaped two-operand steps run on the TMA-staged register-tile kernel
-                                  (pgx_stage.cuh; default 1) */
+#define PGX_OPT_STAGE 9        /* stepwise mode, matrix-product-shaped two-operand steps: 1 (default) the pipelined
+                                  TMA-staged tile kernel k_contract_mm (pgx_mm.cu) | 2 the first-generation staged
+                                  kernel (pgx_stage.cuh) | 0 the streaming kernel only */
+#define PGX_OPT_MMA 10         /* k_contract_mm: fp64 tensor cores (DMMA m8n8k4) for steps whose first operand is a
+                                  batch-invariant table, [M x K] . [K x (N . B)] (default 1; 0 = FMA consumers) */
 
 #define PGX_INFO_N_STEPS 1
 #define PGX_INFO_OUT_ELEMS 2
@@ -128,6 +131,15 @@ int pgx_profile_launches(pgx_plan* plan, const int32_t* ev_states, void* out, vo
 /* Host only (no GPU needed): the tiling the staged GEMM-tile kernel (pgx_stage.cuh) would use for one step record
  * (layout in pgmpy_b200/plan.py). fields[12] = eligible, ax, ay, bx, by, ntx, nty, tiles, sc, swap, form, stage_elems. */
 int pgx_stage_pick(const int32_t* step_record, int32_t item_bytes, int32_t* fields, int64_t* smem_bytes);
+
+/* Host only (no GPU needed): how k_contract_mm (pgx_mm.cu) would run one step record: the step seen as Z matrix
+ * products out_z[M, N] = P_z[M, K] Q_z[K, N] per evidence set. fields[24] = eligible, M, N, Z, K, lgTX, lgTY, TZ, lgKC,
+ * ntx, nty, ntz, n_chunks, n_stages, stage_elems, q_off, p_const, p_base, q_base, o_base, n_active, use_mma,
+ * smem_bytes, n_tiles. tabs (may be NULL; *n_tabs = words needed) receives the offset tables the kernel indexes:
+ * xoffP[M] xoffO[M] yoffQ[N] yoffO[N] soffP[K] soffQ[K] zoffP[Z] zoffQ[Z] zoffO[Z] (table entries), then soffP[K] and
+ * soffQ[K] again in work-table elements (x ldb; ldb = 1 in this host-only call, and 0 for a batch-invariant P). */
+int pgx_mm_pick(const int32_t* step_record, int32_t item_bytes, int32_t allow_mma, int32_t* fields, int32_t* tabs,
+                int64_t tabs_cap, int64_t* n_tabs);
 
 int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value);
 int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value);

@@ -11,6 +11,7 @@ PGX_F64, PGX_F32 = 0, 1
 MODE_AUTO, MODE_STEPWISE, MODE_FUSED = 0, 1, 2
 OPT_MODE, OPT_FUSED_WARPS, OPT_USE_GRAPH, OPT_FUSED_KERNEL, OPT_STEP_KERNEL = 1, 2, 3, 4, 5
 OPT_STAGE = 9
+OPT_MMA = 10
 INFO_N_STEPS, INFO_OUT_ELEMS, INFO_WS_ENTRIES, INFO_LAST_LAUNCHES, INFO_LAST_MODE, INFO_N_EV = 1, 2, 3, 4, 5, 6
 INFO_LAST_VARIANT, INFO_N_LEVELS, INFO_LAST_GRAPH = 7, 8, 9
 INFO_LAST_STAGED_STEPS = 10
@@ -24,6 +25,7 @@ EXPORTS = (
     "pgx_profile_steps",
     "pgx_profile_launches",
     "pgx_stage_pick",
+    "pgx_mm_pick",
     "pgx_plan_set_option",
     "pgx_plan_get_info",
     "pgx_evidence_reduce",
@@ -86,6 +88,8 @@ def load():
     lib.pgx_profile_launches.restype = C.c_int
     lib.pgx_stage_pick.argtypes = [i32p, C.c_int32, i32p, C.POINTER(C.c_int64)]
     lib.pgx_stage_pick.restype = C.c_int
+    lib.pgx_mm_pick.argtypes = [i32p, C.c_int32, C.c_int32, i32p, i32p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.pgx_mm_pick.restype = C.c_int
     lib.pgx_plan_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
     lib.pgx_plan_set_option.restype = C.c_int
     lib.pgx_plan_get_info.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]

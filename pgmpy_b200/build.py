@@ -7,7 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpgx.so")
-SOURCES = [os.path.join(CSRC, "pgx.cu")]
+SOURCES = [os.path.join(CSRC, "pgx.cu"), os.path.join(CSRC, "pgx_mm.cu")]
+OBJ_DIR = os.path.join(CSRC, "_obj")
 
 
 def _headers():
@@ -34,23 +35,30 @@ def needs_build():
 
 
 def build_native(force=False, verbose=False):
+    """One nvcc per translation unit, in parallel, then one link: sm_100a only, -lineinfo for ncu's source page."""
     if not force and not needs_build():
         return LIB
-    cmd = [
-        nvcc_path(),
-        "-gencode", "arch=compute_100a,code=sm_100a",
-        "-O3", "-lineinfo", "-std=c++17",
-        "-Xcompiler", "-fPIC,-O3",
-        "-shared",
-        "-o", LIB,
-    ] + SOURCES
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O3"]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        flags += ["-Xptxas", "-v"]
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, os.path.basename(src) + ".o")
+        procs.append((obj, subprocess.Popen([nvcc_path(), *flags, "-c", src, "-o", obj], stdout=subprocess.PIPE,
+                                            stderr=subprocess.PIPE, text=True)))
+    log = ""
+    for obj, p in procs:
+        so, se = p.communicate()
+        log += so + se
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + so + se)
+    res = subprocess.run([nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [o for o, _ in procs],
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print(log)
     return LIB
 
 

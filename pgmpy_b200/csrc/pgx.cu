@@ -25,6 +25,7 @@
 #include "pgx_step.cuh"
 #include "pgx_fused.cuh"
 #include "pgx_stage.cuh"
+#include "pgx_mm.h"
 
 namespace {
 
@@ -589,7 +590,8 @@ struct LaunchGroup {
     int generic_step = -1;  // >= 0: one launch of the generic kernel for this step
     int first_item = 0, n_items = 0, n_blocks = 0, max_k = 0;
     size_t smem = 0;
-    bool stage = false;  // every step of the group goes to k_contract_stage (TMA-staged GEMM tiles)
+    bool stage = false;  // every step of the group goes to k_contract_stage (first-generation TMA-staged GEMM tiles)
+    bool mm = false;     // every step of the group goes to k_contract_mm (pgx_mm.cu: pipelined matrix-product tiles)
     std::vector<int> step_ids;  // plan steps served by this launch (tracing: pgx_profile_launches)
 };
 
@@ -702,6 +704,18 @@ struct StepSchedule {
     std::vector<LaunchGroup> groups;
     TileItem* d_items = nullptr;
     pgx::StageItem* d_stage_items = nullptr;
+    pgx::MMItem* d_mm_items = nullptr;
+    int32_t* d_mm_tabs = nullptr;
+    void release() {
+        if (d_items) cudaFree(d_items);
+        if (d_stage_items) cudaFree(d_stage_items);
+        if (d_mm_items) cudaFree(d_mm_items);
+        if (d_mm_tabs) cudaFree(d_mm_tabs);
+        d_items = nullptr;
+        d_stage_items = nullptr;
+        d_mm_items = nullptr;
+        d_mm_tabs = nullptr;
+    }
 };
 
 struct GraphEntry {
@@ -737,7 +751,9 @@ struct pgx_plan {
     std::vector<StepSchedule> schedules;
     cudaStream_t cap_stream = nullptr;
     int last_graph = 0;
-    int stage = 1;        // GEMM-shaped two-operand steps go to the TMA-staged register-tile kernel (PGX_OPT_STAGE)
+    int stage = 1;        // matrix-product-shaped two-operand steps: 1 k_contract_mm (default), 2 first-generation
+                          // k_contract_stage, 0 streaming kernel only (PGX_OPT_STAGE)
+    int mma = 1;          // fp64 tensor cores (DMMA) for steps whose P operand is batch invariant (PGX_OPT_MMA)
     int batch_levels = 1; // share one launch among the tile-eligible steps of a dependency level
     cudaEvent_t* prof_events = nullptr;  // set only inside pgx_profile_steps
     int step_kernel = 0;  // 0 = auto (tile-cooperative where possible), 1 = generic per-thread kernel only
@@ -911,10 +927,7 @@ void pgx_plan_destroy(pgx_plan* plan) {
     if (plan->d_pool) cudaFree(plan->d_pool);
     if (plan->d_micro) cudaFree(plan->d_micro);
     for (GraphEntry& g : plan->graphs) cudaGraphExecDestroy(g.exec);
-    for (StepSchedule& c : plan->schedules) {
-        if (c.d_items) cudaFree(c.d_items);
-        if (c.d_stage_items) cudaFree(c.d_stage_items);
-    }
+    for (StepSchedule& c : plan->schedules) c.release();
     if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
     delete plan;
 }
@@ -942,11 +955,14 @@ int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
             plan->use_graph = value ? 1 : 0;
             return PGX_OK;
         case PGX_OPT_STAGE:
-            plan->stage = value ? 1 : 0;
-            for (StepSchedule& c : plan->schedules) {
-                if (c.d_items) cudaFree(c.d_items);
-                if (c.d_stage_items) cudaFree(c.d_stage_items);
+        case PGX_OPT_MMA:
+            if (option == PGX_OPT_STAGE) {
+                if (value < 0 || value > 2) return fail(PGX_ERR_INVALID, "stage must be 0, 1 or 2");
+                plan->stage = (int)value;
+            } else {
+                plan->mma = value ? 1 : 0;
             }
+            for (StepSchedule& c : plan->schedules) c.release();
             plan->schedules.clear();
             for (GraphEntry& g : plan->graphs) cudaGraphExecDestroy(g.exec);
             plan->graphs.clear();
@@ -980,7 +996,7 @@ int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value) {
             int64_t n = 0;
             if (plan->last_mode == PGX_MODE_STEPWISE && plan->last_sched >= 0 && plan->last_sched < (int)plan->schedules.size())
                 for (const LaunchGroup& g : plan->schedules[plan->last_sched].groups)
-                    if (g.stage) n += g.n_items;
+                    if (g.stage || g.mm) n += g.n_items;
             *value = n;
             break;
         }
@@ -1082,13 +1098,13 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
         // launch schedule for this batch size: tile-eligible steps of one dependency level share a launch
         StepSchedule* sched = nullptr;
         for (StepSchedule& c : pl->schedules)
-            if (c.B == B && c.step_kernel == pl->step_kernel + 4 * pl->batch_levels + 32 * pl->stage &&
+            if (c.B == B && c.step_kernel == pl->step_kernel + 4 * pl->batch_levels + 32 * pl->stage + 128 * pl->mma &&
                 c.dtype_size == (int)sizeof(T))
                 sched = &c;
         if (!sched) {
             StepSchedule ns;
             ns.B = B;
-            ns.step_kernel = pl->step_kernel + 4 * pl->batch_levels + 32 * pl->stage;
+            ns.step_kernel = pl->step_kernel + 4 * pl->batch_levels + 32 * pl->stage + 128 * pl->mma;
             const int64_t tile_b_tiles = b_tiles;
             ns.dtype_size = (int)sizeof(T);
             std::vector<TileItem> items;
@@ -1108,6 +1124,10 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
             // ... and one group of steps for the TMA-staged GEMM-tile kernel
             LaunchGroup cur_stage;
             std::vector<StageItem> stage_items, pending_stage;
+            LaunchGroup cur_mm;
+            std::vector<MMItem> mm_items, pending_mm;
+            std::vector<double> pending_mm_cost;
+            std::vector<int32_t> mm_tabs;
             const bool stage_on = pl->stage && pl->step_kernel == 0 && bt_log2 == 5 &&
                                   ws_off0 + (size_t)pl->ws_entries * (size_t)ldb < (1ULL << 32) && pl->ws_entries < (1LL << 31);
             int cur_level = -1;
@@ -1120,6 +1140,36 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                     ns.groups.push_back(cur_stage);
                 }
                 cur_stage = LaunchGroup();
+                if (cur_mm.n_items > 0) {
+                    // split every step's tiles into CTA-sized runs. One CTA per SM is resident (the stage ring takes the
+                    // shared memory), so the launch gets a whole number of waves: `waves` x 148 CTAs dealt to the steps in
+                    // proportion to their model cost, a run never shorter than ~20k model cycles (pipeline prologue).
+                    double total = 0;
+                    for (size_t i = 0; i < pending_mm.size(); ++i) total += pending_mm_cost[i] * (double)b_tiles;
+                    int waves = (int)(total / (148.0 * 100000.0));
+                    waves = waves < 1 ? 1 : (waves > 6 ? 6 : waves);
+                    const double target = std::max(20000.0, total / (148.0 * waves));
+                    int nb = 0;
+                    for (size_t i = 0; i < pending_mm.size(); ++i) {
+                        MMItem& mi = pending_mm[i];
+                        const int64_t tiles = (int64_t)mi.n_tiles * b_tiles;
+                        const double per_tile = pending_mm_cost[i] / (double)mi.n_tiles;
+                        int64_t want = (int64_t)(per_tile * (double)tiles / target + 0.5);  // CTAs for this step
+                        want = std::max<int64_t>(1, std::min<int64_t>(want, tiles));
+                        const int64_t tpc = (tiles + want - 1) / want;
+                        mi.tiles_per_cta = (int32_t)tpc;
+                        mi.n_ctas = (int32_t)((tiles + tpc - 1) / tpc);
+                        mi.blk_begin = nb;
+                        nb += mi.n_ctas;
+                    }
+                    cur_mm.n_blocks = nb;
+                    cur_mm.first_item = (int)mm_items.size();
+                    mm_items.insert(mm_items.end(), pending_mm.begin(), pending_mm.end());
+                    pending_mm.clear();
+                    pending_mm_cost.clear();
+                    ns.groups.push_back(cur_mm);
+                }
+                cur_mm = LaunchGroup();
             };
             for (size_t si = 0; si < pl->steps.size(); ++si) {
                 const StepInfo& s = pl->steps[si];
@@ -1128,7 +1178,22 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                 const int32_t* srec = pl->pool.data() + s.rec_off;
                 if (s.level != cur_level || !pl->batch_levels) flush_level();
                 cur_level = s.level;
-                if (stage_on && tile_ok) {
+                if (stage_on && pl->stage == 1) {
+                    MMChoice ch;
+                    if (mm_pick(srec, sizeof(T), pl->mma != 0, ldb, ch) &&
+                        (int64_t)ch.item.n_tiles * b_tiles < (1LL << 30) && mm_tabs.size() + ch.tabs.size() < (1u << 30)) {
+                        ch.item.tab = (int32_t)mm_tabs.size();
+                        mm_tabs.insert(mm_tabs.end(), ch.tabs.begin(), ch.tabs.end());
+                        pending_mm.push_back(ch.item);
+                        pending_mm_cost.push_back(ch.cost);
+                        cur_mm.mm = true;
+                        cur_mm.step_ids.push_back((int)si);
+                        cur_mm.n_items += 1;
+                        cur_mm.smem = std::max(cur_mm.smem, ch.smem);
+                        continue;
+                    }
+                }
+                if (stage_on && pl->stage == 2 && tile_ok) {
                     StageItem sit;
                     size_t sm = 0;
                     if (pick_stage(srec, s.out_size, s.sum_size, sizeof(T), sit, sm)) {
@@ -1188,9 +1253,14 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                 PGX_CUDA(cudaMalloc((void**)&ns.d_stage_items, stage_items.size() * sizeof(StageItem)));
                 PGX_CUDA(cudaMemcpy(ns.d_stage_items, stage_items.data(), stage_items.size() * sizeof(StageItem), cudaMemcpyHostToDevice));
             }
+            if (!mm_items.empty()) {
+                PGX_CUDA(cudaMalloc((void**)&ns.d_mm_items, mm_items.size() * sizeof(MMItem)));
+                PGX_CUDA(cudaMemcpy(ns.d_mm_items, mm_items.data(), mm_items.size() * sizeof(MMItem), cudaMemcpyHostToDevice));
+                PGX_CUDA(cudaMalloc((void**)&ns.d_mm_tabs, std::max<size_t>(1, mm_tabs.size()) * sizeof(int32_t)));
+                PGX_CUDA(cudaMemcpy(ns.d_mm_tabs, mm_tabs.data(), mm_tabs.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            }
             if (pl->schedules.size() >= 8) {
-                if (pl->schedules.front().d_items) cudaFree(pl->schedules.front().d_items);
-                if (pl->schedules.front().d_stage_items) cudaFree(pl->schedules.front().d_stage_items);
+                pl->schedules.front().release();
                 pl->schedules.erase(pl->schedules.begin());
                 for (GraphEntry& g : pl->graphs) cudaGraphExecDestroy(g.exec);  // graphs reference the item tables
                 pl->graphs.clear();
@@ -1228,6 +1298,9 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                     else
                         PGX_LAUNCH_STEP(MAX_OPS);
 #undef PGX_LAUNCH_STEP
+                } else if (g.mm) {
+                    mm_launch(sizeof(T), sched->d_mm_items + g.first_item, g.n_items, g.n_blocks, g.smem, sched->d_mm_tabs, ws_all,
+                              (uint32_t)ws_off0, B, (uint32_t)ldb, (int)b_tiles, qs);
                 } else if (g.stage) {
                     if (g.smem > 48 * 1024)
                         cudaFuncSetAttribute(k_contract_stage<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
@@ -1404,6 +1477,24 @@ int pgx_stage_pick(const int32_t* step_record, int32_t item_bytes, int32_t* fiel
     *smem_bytes = (int64_t)sm;
     const int32_t f[12] = {ok ? 1 : 0, it.ax, it.ay, it.bx, it.by, it.ntx, it.nty, it.tiles, it.sc, it.swap, it.form, it.stage_elems};
     for (int i = 0; i < 12; ++i) fields[i] = f[i];
+    return PGX_OK;
+}
+
+int pgx_mm_pick(const int32_t* step_record, int32_t item_bytes, int32_t allow_mma, int32_t* fields, int32_t* tabs,
+                int64_t tabs_cap, int64_t* n_tabs) {
+    if (!step_record || !fields || !n_tabs || (item_bytes != 4 && item_bytes != 8)) return fail(PGX_ERR_INVALID, "bad argument");
+    pgx::MMChoice ch;
+    const bool ok = pgx::mm_pick(step_record, (size_t)item_bytes, allow_mma != 0, 1, ch);
+    for (int i = 0; i < 24; ++i) fields[i] = 0;
+    *n_tabs = 0;
+    if (!ok) return PGX_OK;
+    const pgx::MMItem& it = ch.item;
+    const int32_t f[24] = {1, it.M, it.N, it.Z, it.K, it.lgTX, it.lgTY, it.TZ, it.lgKC, it.ntx, it.nty, it.ntz, it.n_chunks,
+                           it.n_stages, it.stage_elems, it.q_off, it.p_const, (int32_t)it.p_base, (int32_t)it.q_base,
+                           (int32_t)it.o_base, it.n_active, it.use_mma, (int32_t)ch.smem, it.n_tiles};
+    for (int i = 0; i < 24; ++i) fields[i] = f[i];
+    *n_tabs = (int64_t)ch.tabs.size();
+    if (tabs && tabs_cap >= (int64_t)ch.tabs.size()) std::memcpy(tabs, ch.tabs.data(), ch.tabs.size() * sizeof(int32_t));
     return PGX_OK;
 }
 

@@ -93,9 +93,14 @@ class CompiledPlan:
         v = self.info(N.INFO_LAST_VARIANT)
         return {0: "stepwise", 1: "generic", 2: "tables-smem", 3: "tables-global"}[v]
 
-    def set_stage(self, enabled: bool = True):
-        """GEMM-shaped two-operand steps on the TMA-staged register-tile kernel (default on)."""
-        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_STAGE, 1 if enabled else 0))
+    def set_stage(self, which=1):
+        """Matrix-product-shaped two-operand steps: 1/True the pipelined TMA-staged tile kernel k_contract_mm (default),
+        2 the first-generation staged kernel, 0/False the streaming kernel only."""
+        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_STAGE, int(which)))
+
+    def set_mma(self, enabled: bool = True):
+        """fp64 tensor cores (DMMA) for k_contract_mm steps with a batch-invariant first operand (default on)."""
+        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_MMA, 1 if enabled else 0))
 
     def set_graph(self, enabled: bool = True):
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_USE_GRAPH, 1 if enabled else 0))

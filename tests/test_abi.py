@@ -111,3 +111,91 @@ def test_stage_pick_finds_the_gemm_shape_of_a_two_operand_step():
     assert ok == 1 and {ax, ay} == {0, 1} and form == 1 * 4 + 2
     assert 1 <= bx * by <= 8 and ntx * 4 * bx >= card["x" if ax == 0 else "y"] and 1 <= sc <= 96
     assert 0 < sm.value <= 200 * 1024 and tiles == ntx * nty
+
+
+def _mm_pick(rec, item_bytes=8, allow_mma=1):
+    import ctypes as C
+
+    lib = N.load()
+    f = (C.c_int32 * 24)()
+    n = C.c_int64()
+    ptr = rec.ctypes.data_as(C.POINTER(C.c_int32))
+    assert lib.pgx_mm_pick(ptr, item_bytes, allow_mma, f, None, 0, C.byref(n)) == 0
+    if not f[0]:
+        return None, None
+    tabs = np.zeros(n.value, dtype=np.int32)
+    assert lib.pgx_mm_pick(ptr, item_bytes, allow_mma, f, tabs.ctypes.data_as(C.POINTER(C.c_int32)), tabs.size, C.byref(n)) == 0
+    keys = ("ok M N Z K lgTX lgTY TZ lgKC ntx nty ntz n_chunks n_stages stage_elems q_off p_const p_base q_base o_base "
+            "n_active use_mma smem n_tiles").split()
+    return dict(zip(keys, list(f))), tabs
+
+
+@pytest.mark.parametrize("name", ["pathfinder", "diabetes", "munin"])
+def test_mm_pick_tables_reproduce_the_step_definition(name):
+    """Host-only (pgx_mm_pick, no GPU): for every step of a real junction-tree plan that k_contract_mm would take, the
+    offset tables it indexes (flattened M/N/Z/K -> entries of P, Q and the output) must address exactly the entries the
+    step record's mixed-radix definition does, the tiling must cover the index space and fit shared memory."""
+    from pgmpy_b200.evidence import sample_evidence
+    from pgmpy_b200.plan import OP_FIXED, STEP_FIXED
+    from pgmpy_b200.planner import JTStructure, compile_jt_plan
+    import pgmpy_b200 as px
+
+    m = px.get_example_model(name)
+    ev_vars, _ = sample_evidence(m, 1, 8, seed=1)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars)
+    pool = np.ascontiguousarray(plan.pool, dtype=np.int32)
+    rng = np.random.default_rng(0)
+    taken = mma = 0
+    shapes = set()
+    for si in range(plan.n_steps):
+        rec = pool[int(pool[pool[10] + si]):]
+        A, S, K2 = int(rec[0]), int(rec[1]), int(rec[2])
+        f, tabs = _mm_pick(rec)
+        if f is None:
+            continue
+        taken += 1
+        mma += f["use_mma"]
+        M, Nn, Z, K = f["M"], f["N"], f["Z"], f["K"]
+        key = (M, Nn, Z, K, f["p_const"])
+        if key in shapes and taken > 40:
+            continue  # the same shape repeats per time slice: check a few of each
+        shapes.add(key)
+        odims = rec[STEP_FIXED:STEP_FIXED + A].astype(np.int64)
+        sdims = rec[STEP_FIXED + A:STEP_FIXED + A + S].astype(np.int64)
+        assert M * Nn * Z == int(np.prod(odims)) and K == int(np.prod(sdims))
+        opw = OP_FIXED + A + S
+        ops = [rec[STEP_FIXED + A + S + k * opw:][:opw].astype(np.int64) for k in range(2)]
+        # the definition: every (o, s) pair -> (entry of op0, entry of op1), products summed per o
+        o_idx = np.stack(np.unravel_index(np.arange(M * Nn * Z), odims), axis=1) if A else np.zeros((1, 0), np.int64)
+        s_idx = np.stack(np.unravel_index(np.arange(K), sdims), axis=1)
+        ent = []
+        for op in ops:
+            base = int(op[1])
+            eo = o_idx @ op[OP_FIXED:OP_FIXED + A]
+            es = s_idx @ op[OP_FIXED + A:OP_FIXED + A + S]
+            ent.append(base + eo[:, None] + es[None, :])
+        size = [int(e.max()) + 1 for e in ent]
+        vals = [rng.random(n) for n in size]
+        want = (vals[0][ent[0]] * vals[1][ent[1]]).sum(axis=1)
+        # the kernel's addressing
+        t = np.split(tabs, np.cumsum([M, M, Nn, Nn, K, K, Z, Z, Z, K]))
+        xoffP, xoffO, yoffQ, yoffO, soffP, soffQ, zoffP, zoffQ, zoffO, soffPl, soffQl = t
+        assert (soffQl == soffQ).all() and (soffPl == (0 if f["p_const"] else soffP)).all()  # ldb = 1 here
+        swapped = f["p_base"] != int(ops[0][1]) or (int(ops[0][1]) == int(ops[1][1]) and False)
+        pv, qv = (vals[1], vals[0]) if swapped else (vals[0], vals[1])
+        pe = f["p_base"] + zoffP[:, None, None] + xoffP[None, :, None] + soffP[None, None, :]
+        qe = f["q_base"] + zoffQ[:, None, None] + yoffQ[None, :, None] + soffQ[None, None, :]
+        got = np.einsum("zxk,zyk->zxy", pv[pe], qv[qe])
+        oe = zoffO[:, None, None] + xoffO[None, :, None] + yoffO[None, None, :]
+        assert sorted(oe.reshape(-1)) == list(range(M * Nn * Z))  # a bijection onto the output entries
+        flat = np.empty(M * Nn * Z)
+        flat[oe.reshape(-1)] = got.reshape(-1)
+        np.testing.assert_allclose(flat, want, rtol=1e-12)
+        # tiling: covers the index space, fits the budget, one register block per active warp
+        TX, TY = 1 << f["lgTX"], 1 << f["lgTY"]
+        assert f["ntx"] * TX >= M and f["nty"] * TY >= Nn and f["ntz"] * f["TZ"] >= Z
+        assert f["n_active"] == f["TZ"] * TX * TY // 32 <= 16 and 1 <= f["n_stages"] <= 8
+        assert f["smem"] <= 227 * 1024 and (f["n_chunks"] << f["lgKC"]) >= K
+    assert taken > 0
+    if name == "diabetes":
+        assert mma > 0  # CPT-times-message steps go to the tensor-core consumer

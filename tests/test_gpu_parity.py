@@ -149,25 +149,30 @@ def test_bp_marginals_batch_vs_reference_bp_query(torch_cuda, name):
 
 
 @pytest.mark.parametrize("name,B", [("pathfinder", 40), ("diabetes", 96), ("munin", 64)])
-def test_staged_gemm_tile_kernel_matches(torch_cuda, name, B):
-    """GEMM-shaped two-operand steps on the TMA-staged register-tile kernel (pgx_stage.cuh) vs the streaming tile kernel
-    (itself pinned to the oracle and the reference goldens), incl. a partial last tile of evidence sets; pathfinder also
-    against the numpy plan interpreter."""
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_matrix_product_tile_kernel_matches(torch_cuda, name, B, dtype):
+    """Matrix-product-shaped two-operand steps on k_contract_mm (pgx_mm.cu: TMA-staged operand rows, 4 x 8 register
+    blocks, DMMA for a batch-invariant first operand) vs the streaming tile kernel (itself pinned to the oracle and the
+    reference goldens), incl. a partial last tile of evidence sets; tensor-core and FMA consumers, the first-generation
+    staged kernel, and the numpy plan interpreter on the smaller models."""
     m = px.get_example_model(name)
     jt = JTStructure.from_model(m)
     ev_vars, states = sample_evidence(m, B, 8, seed=3)
     plan = compile_jt_plan(jt, ev_vars)
-    cp = _engine()(plan)
+    cp = _engine()(plan, dtype=dtype)
+    tol = 1e-13 if dtype == "float64" else 2e-5
     cp.set_mode("stepwise")
-    cp.set_stage(False)
+    cp.set_stage(0)
     base = cp.run_host(states)
     assert cp.last_staged_steps == 0
-    cp.set_stage(True)
-    got = cp.run_host(states)
-    assert cp.last_staged_steps > 0, "no step was routed to the staged kernel"
-    assert np.isfinite(got).all()
-    assert rel_err(got, base) <= 1e-13
-    if name == "pathfinder":
+    for which, mma in ((1, True), (1, False), (2, True)):
+        cp.set_stage(which)
+        cp.set_mma(mma)
+        got = cp.run_host(states)
+        assert cp.last_staged_steps > 0, "no step was routed to the matrix-product kernel"
+        assert np.isfinite(got).all()
+        assert rel_err(got, base) <= tol, (which, mma)
+    if name == "pathfinder" and dtype == "float64":
         assert rel_err(got, run_plan(plan.pool, plan.const_blob, states)) <= 1e-12
 
 
