@@ -86,6 +86,7 @@ extern "C" {
 #define PGX_INFO_LAST_VARIANT 7 /* which fused kernel ran (PGX_OPT_FUSED_KERNEL numbering), 0 if stepwise */
 #define PGX_INFO_LAST_GRAPH 9    /* 1 if the most recent stepwise run was a CUDA-graph replay */
 #define PGX_INFO_LAST_STAGED_STEPS 10 /* steps the most recent stepwise run sent to the TMA-staged GEMM-tile kernel */
+#define PGX_INFO_IN_ELEMS 11    /* elements of one row of `soft` (0: the plan has no input tables) */
 #define PGX_INFO_N_LEVELS 8     /* dependency levels of the plan (0 when no offset tables were built) */
 
 typedef struct pgx_plan pgx_plan; /* opaque */
@@ -115,6 +116,14 @@ size_t pgx_workspace_bytes(const pgx_plan* plan, int64_t B);
  * Asynchronous: returns after enqueueing. */
 int pgx_run_batch(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
                   int64_t B, void* stream);
+
+/* The same for a plan with batch-dependent INPUT tables (soft / virtual evidence, pgmpy/inference/base.py:256-299:
+ * one likelihood vector per soft-evidence variable, which the reference adds as an observed binary child per query):
+ *   soft       DEVICE dtype [B, in_elems]   row b = the input tables of evidence set b (PGX_INFO_IN_ELEMS, layout in
+ *                                           the plan's inputs block, pgmpy_b200/plan.py)
+ * pgx_run_batch on such a plan is an error; `soft` must be NULL for a plan without input tables. */
+int pgx_run_batch_soft(pgx_plan* plan, const int32_t* ev_states, const void* soft, void* out, void* workspace,
+                       size_t workspace_bytes, int64_t B, void* stream);
 
 /* Tracing aid: runs the plan in stepwise mode with a CUDA event after every step and returns the per-step device
  * time in milliseconds (step_ms[n_steps], n_steps >= the plan's step count). Synchronises the stream. */

@@ -57,6 +57,15 @@ def parse(pool):
     for g in range(hdr["n_segs"]):
         sb = hdr["segs_off"] + g * P.SEG_WORDS
         segs.append(dict(off=_i64(pool, sb), size=int(pool[sb + 2]), out_off=int(pool[sb + 3]), flags=int(pool[sb + 4])))
+    inputs = []
+    ib = int(pool[15])
+    hdr["in_elems"] = 0
+    if ib:
+        hdr["in_elems"] = int(pool[ib + 1])
+        for j in range(int(pool[ib])):
+            at = ib + 2 + 4 * j
+            inputs.append(dict(off=_i64(pool, at), size=int(pool[at + 2]), in_off=int(pool[at + 3])))
+    hdr["inputs"] = inputs
     return hdr, steps, segs
 
 
@@ -68,8 +77,8 @@ def _grid(dims, strides):
     return off
 
 
-def run_plan(pool, const_blob, ev_states, dtype=np.float64, return_workspace=False):
-    """Returns out[B, out_elems]. ev_states: int [B, n_ev]."""
+def run_plan(pool, const_blob, ev_states, dtype=np.float64, return_workspace=False, soft=None):
+    """Returns out[B, out_elems]. ev_states: int [B, n_ev]; soft: [B, in_elems] rows for the plan's input tables."""
     hdr, steps, segs = parse(pool)
     ev_states = np.asarray(ev_states, dtype=np.int64).reshape(-1, max(hdr["n_ev"], 0)) if hdr["n_ev"] else np.zeros(
         (np.asarray(ev_states).shape[0], 0), dtype=np.int64
@@ -78,6 +87,10 @@ def run_plan(pool, const_blob, ev_states, dtype=np.float64, return_workspace=Fal
     const = np.asarray(const_blob, dtype=dtype)
     ws = np.zeros((hdr["ws_entries"], B), dtype=dtype)
     bidx = np.arange(B)
+    if hdr["inputs"]:
+        soft = np.asarray(soft, dtype=dtype).reshape(B, hdr["in_elems"])
+        for inp in hdr["inputs"]:
+            ws[inp["off"] : inp["off"] + inp["size"], :] = soft[:, inp["in_off"] : inp["in_off"] + inp["size"]].T
     for st in steps:
         O, S_ = st["out_size"], st["sum_size"]
         num = np.ones((B, O, S_), dtype=dtype)

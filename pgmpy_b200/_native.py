@@ -15,6 +15,7 @@ OPT_MMA = 10
 INFO_N_STEPS, INFO_OUT_ELEMS, INFO_WS_ENTRIES, INFO_LAST_LAUNCHES, INFO_LAST_MODE, INFO_N_EV = 1, 2, 3, 4, 5, 6
 INFO_LAST_VARIANT, INFO_N_LEVELS, INFO_LAST_GRAPH = 7, 8, 9
 INFO_LAST_STAGED_STEPS = 10
+INFO_IN_ELEMS = 11
 FUSED_KERNELS = {"auto": 0, "generic": 1, "tables-smem": 2, "tables-global": 3}
 
 EXPORTS = (
@@ -22,6 +23,7 @@ EXPORTS = (
     "pgx_plan_destroy",
     "pgx_workspace_bytes",
     "pgx_run_batch",
+    "pgx_run_batch_soft",
     "pgx_profile_steps",
     "pgx_profile_launches",
     "pgx_stage_pick",
@@ -77,6 +79,8 @@ def load():
     lib.pgx_workspace_bytes.restype = C.c_size_t
     lib.pgx_run_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p]
     lib.pgx_run_batch.restype = C.c_int
+    lib.pgx_run_batch_soft.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p]
+    lib.pgx_run_batch_soft.restype = C.c_int
     lib.pgx_profile_steps.argtypes = [
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p, C.POINTER(C.c_float), C.c_int32,
     ]

@@ -541,6 +541,25 @@ __global__ void __launch_bounds__(256) k_evidence_gather(const T* __restrict__ t
     dst[(int64_t)e * ldb + b] = table[off];
 }
 
+// Batch-dependent input tables (soft evidence): ws[(off_j + i), b] = soft[b, in_off_j + i]. One launch for all inputs of
+// the plan: thread = (evidence set, element of the input row), reads coalesced along the row.
+template <typename T>
+__global__ void __launch_bounds__(256) k_scatter_inputs(const int32_t* __restrict__ inputs, const T* __restrict__ soft,
+                                                        T* __restrict__ ws, int64_t B, int64_t ldb) {
+    const int n_in = inputs[0], in_elems = inputs[1];
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * in_elems) return;
+    const int64_t b = idx / in_elems;
+    const int e = (int)(idx - b * in_elems);
+    for (int j = 0; j < n_in; ++j) {
+        const int32_t* r = inputs + 2 + 4 * j;
+        if (e >= r[3] && e < r[3] + r[2]) {
+            ws[(ld_i64(r) + (e - r[3])) * ldb + b] = soft[idx];
+            return;
+        }
+    }
+}
+
 // first index of the row maximum (numpy.argmax semantics: first occurrence; NaN propagates like numpy: a NaN wins)
 template <typename T>
 __global__ void __launch_bounds__(128) k_argmax_rows(const T* __restrict__ src, int64_t n, int64_t B, int32_t* __restrict__ out) {
@@ -721,6 +740,7 @@ struct StepSchedule {
 struct GraphEntry {
     int64_t B;
     const void* ev;
+    const void* soft;
     void* out;
     void* ws;
     int step_kernel;
@@ -735,6 +755,7 @@ struct pgx_plan {
     int n_ev = 0, n_steps = 0, n_segs = 0, out_elems = 0;
     int64_t ws_entries = 0, table_entries = 0;
     int step_index_off = 0, segs_off = 0, ev_card_off = 0, max_ops = 0;
+    int inputs_off = 0, n_inputs = 0, in_elems = 0;  // batch-dependent input tables (soft evidence)
     std::vector<int32_t> pool;
     std::vector<StepInfo> steps;
     int32_t* d_pool = nullptr;
@@ -892,6 +913,20 @@ int pgx_plan_create(const pgx_plan_desc* desc, pgx_plan** out) {
         out_total += sg[2];
     }
     (void)out_total;
+    pl->inputs_off = p[15];
+    if (pl->inputs_off != 0) {
+        if (pl->inputs_off < HEADER_WORDS || (int64_t)pl->inputs_off + 2 > W) return bad(PGX_ERR_INVALID, "inputs block out of pool");
+        pl->n_inputs = p[pl->inputs_off];
+        pl->in_elems = p[pl->inputs_off + 1];
+        if (pl->n_inputs < 1 || pl->in_elems < 1 || (int64_t)pl->inputs_off + 2 + 4LL * pl->n_inputs > W)
+            return bad(PGX_ERR_INVALID, "inputs block out of pool");
+        for (int j = 0; j < pl->n_inputs; ++j) {
+            const int32_t* r = p + pl->inputs_off + 2 + 4 * j;
+            const int64_t off = ld_i64(r);
+            if (off < 0 || r[2] < 1 || off + r[2] > pl->ws_entries) return bad(PGX_ERR_BOUNDS, "input table outside workspace");
+            if (r[3] < 0 || r[3] + r[2] > pl->in_elems) return bad(PGX_ERR_BOUNDS, "input table outside the input row");
+        }
+    }
     pl->pool.assign(p, p + W);
     std::vector<int32_t> micro_words;
     if (pl->n_steps > 0 && pl->max_joint <= (1 << 16)) {
@@ -991,6 +1026,7 @@ int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value) {
         case PGX_INFO_N_EV: *value = plan->n_ev; break;
         case PGX_INFO_LAST_VARIANT: *value = plan->last_variant; break;
         case PGX_INFO_LAST_GRAPH: *value = plan->last_graph; break;
+        case PGX_INFO_IN_ELEMS: *value = plan->in_elems; break;
         case PGX_INFO_N_LEVELS: *value = plan->micro.ok ? plan->micro.n_levels : 0; break;
         case PGX_INFO_LAST_STAGED_STEPS: {
             int64_t n = 0;
@@ -1010,7 +1046,10 @@ int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value) {
 namespace {
 
 template <typename T>
-int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t B, cudaStream_t st) {
+int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, void* ws_v, int64_t B, cudaStream_t st) {
+    const T* soft = (const T*)soft_v;
+    const int32_t* d_inputs = pl->n_inputs ? pl->d_pool + pl->inputs_off : nullptr;
+    const unsigned in_blocks = pl->n_inputs ? (unsigned)((B * pl->in_elems + 255) / 256) : 0u;
     const int64_t ldb = pgx_batch_ld(B);
     const T* cst = (const T*)pl->blob;
     T* ws_all = (T*)ws_v;
@@ -1052,7 +1091,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
         if (G > 16) G = 16;
 #define PGX_LAUNCH_FUSED2(SM, FO)                                                                                     \
     k_plan_fused2<T, SM, FO><<<(unsigned)rows, 32 * G, dyn, st>>>(pl->d_micro, cst, ws, ev, pl->d_pool + pl->ev_card_off, out, \
-                                                                  pl->n_ev, (int)pl->ws_entries, B, ldb)
+                                                                  pl->n_ev, (int)pl->ws_entries, B, ldb, soft, d_inputs)
         if (smem && pl->micro.all_fast) {
             PGX_CUDA(cudaFuncSetAttribute(k_plan_fused2<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             PGX_LAUNCH_FUSED2(true, true);
@@ -1081,6 +1120,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
             G = 16;
         }
         dim3 block(32, G);
+        if (pl->n_inputs) k_scatter_inputs<T><<<in_blocks, 256, 0, st>>>(d_inputs, soft, ws, B, ldb);
         if (pl->max_ops <= 4)
             k_plan_fused<T, 4><<<(unsigned)rows, block, 0, st>>>(pl->d_pool, cst, ws, ev, out, B, ldb);
         else if (pl->max_ops <= 8)
@@ -1277,6 +1317,10 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
             cudaEvent_t* evs = pl->prof_events;
             int ev_idx = 0;
             if (idx32) cudaMemcpyAsync(ws_all, cst, (size_t)pl->table_entries * sizeof(T), cudaMemcpyDeviceToDevice, qs);
+            if (pl->n_inputs) {
+                k_scatter_inputs<T><<<in_blocks, 256, 0, qs>>>(d_inputs, soft, ws, B, ldb);
+                ++n;
+            }
             for (const LaunchGroup& g : sched->groups) {
                 if (g.generic_step >= 0) {
                     const StepInfo& s = pl->steps[g.generic_step];
@@ -1346,7 +1390,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
             // replay the launch sequence as a CUDA graph (captured once per argument tuple)
             GraphEntry* hit = nullptr;
             for (GraphEntry& g : pl->graphs)
-                if (g.B == B && g.ev == (const void*)ev && g.out == out_v && g.ws == ws_v && g.step_kernel == pl->step_kernel &&
+                if (g.B == B && g.ev == (const void*)ev && g.soft == soft_v && g.out == out_v && g.ws == ws_v && g.step_kernel == pl->step_kernel &&
                     g.dtype_size == (int)sizeof(T))
                     hit = &g;
             if (!hit) {
@@ -1364,7 +1408,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, void* out_v, void* ws_v, int64_t 
                             cudaGraphExecDestroy(pl->graphs.front().exec);
                             pl->graphs.erase(pl->graphs.begin());
                         }
-                        pl->graphs.push_back(GraphEntry{B, (const void*)ev, out_v, ws_v, pl->step_kernel, (int)sizeof(T), n, exec});
+                        pl->graphs.push_back(GraphEntry{B, (const void*)ev, soft_v, out_v, ws_v, pl->step_kernel, (int)sizeof(T), n, exec});
                         hit = &pl->graphs.back();
                     }
                 }
@@ -1394,15 +1438,22 @@ extern "C" {
 
 int pgx_run_batch(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
                   int64_t B, void* stream) {
+    return pgx_run_batch_soft(plan, ev_states, nullptr, out, workspace, workspace_bytes, B, stream);
+}
+
+int pgx_run_batch_soft(pgx_plan* plan, const int32_t* ev_states, const void* soft, void* out, void* workspace,
+                       size_t workspace_bytes, int64_t B, void* stream) {
     if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+    if (plan->n_inputs > 0 && !soft) return fail(PGX_ERR_INVALID, "plan has soft-evidence input tables but `soft` is null");
+    if (plan->n_inputs == 0 && soft) return fail(PGX_ERR_INVALID, "plan has no soft-evidence input tables");
     if (B <= 0) return fail(PGX_ERR_INVALID, "batch must be positive");
     if (plan->n_ev > 0 && !ev_states) return fail(PGX_ERR_INVALID, "plan has evidence slots but ev_states is null");
     if (!out && plan->out_elems > 0) return fail(PGX_ERR_INVALID, "null output");
     if (!workspace || workspace_bytes < pgx_workspace_bytes(plan, B))
         return fail(PGX_ERR_WORKSPACE, "workspace too small: need " + std::to_string(pgx_workspace_bytes(plan, B)) + " bytes");
     cudaStream_t st = (cudaStream_t)stream;
-    if (plan->dtype == PGX_F64) return run_typed<double>(plan, ev_states, out, workspace, B, st);
-    return run_typed<float>(plan, ev_states, out, workspace, B, st);
+    if (plan->dtype == PGX_F64) return run_typed<double>(plan, ev_states, soft, out, workspace, B, st);
+    return run_typed<float>(plan, ev_states, soft, out, workspace, B, st);
 }
 
 // Shared body of the two tracing entry points: a stepwise pass with one CUDA event per launch.

@@ -376,7 +376,8 @@ template <typename T, bool SMEM, bool FAST_ONLY>
 __global__ void __launch_bounds__(512, FAST_ONLY ? PGX_FUSED_FAST_MINB : 1) k_plan_fused2(const int32_t* __restrict__ mp, const T* __restrict__ cst,
                                                      T* __restrict__ ws_g, const int32_t* __restrict__ ev,
                                                      const int32_t* __restrict__ ev_card, T* __restrict__ out, int n_ev,
-                                                     int ws_entries, int64_t B, int64_t ldb) {
+                                                     int ws_entries, int64_t B, int64_t ldb,
+                                                     const T* __restrict__ soft, const int32_t* __restrict__ inputs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* ws_s = reinterpret_cast<T*>(smem_raw);
     int32_t* evs = reinterpret_cast<int32_t*>(smem_raw + (SMEM ? (size_t)ws_entries * FUSED_LANES * sizeof(T) : 0));
@@ -395,6 +396,24 @@ __global__ void __launch_bounds__(512, FAST_ONLY ? PGX_FUSED_FAST_MINB : 1) k_pl
             st = st < 0 ? 0 : (st >= card ? card - 1 : st);
         }
         evs[sl * FUSED_LANES + bb] = st;
+    }
+    if (inputs != nullptr) {
+        // batch-dependent input tables (soft evidence): the CTA's 32 rows of soft[B, in_elems] -> work entries
+        const int n_in = __ldg(inputs), in_elems = __ldg(inputs + 1);
+        for (int i = threadIdx.x; i < FUSED_LANES * in_elems; i += blockDim.x) {
+            const int bb = i / in_elems, e = i - bb * in_elems;
+            if (row0 + bb >= B) continue;
+            const T v = soft[(row0 + bb) * in_elems + e];
+            for (int j = 0; j < n_in; ++j) {
+                const int32_t* r = inputs + 2 + 4 * j;
+                const int in_off = __ldg(r + 3), size = __ldg(r + 2);
+                if (e >= in_off && e < in_off + size) {
+                    const int entry = __ldg(r) + (e - in_off);
+                    if (SMEM) ws_s[entry * FUSED_LANES + bb] = v; else ws_g[(int64_t)entry * ldb + row0 + bb] = v;
+                    break;
+                }
+            }
+        }
     }
     __syncthreads();
     T* wsb = SMEM ? ws_s + lane : ws_g + (b < B ? b : 0);

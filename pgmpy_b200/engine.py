@@ -122,12 +122,24 @@ class CompiledPlan:
     MAX_WORKSPACE_BYTES = 31 << 30  # also keeps every element index of the 32-bit-addressed step kernel below 2^32
     MAX_ROWS_PER_PASS = 1 << 20  # the stepwise grid covers at most 65 535 tiles of 32 evidence sets
 
-    def run(self, ev_states, out=None, workspace=None):
+    def run(self, ev_states, out=None, workspace=None, soft=None):
         """ev_states: int32 CUDA tensor [B, n_ev] (or [B, 0] / None with B given by `out`).
+        soft: CUDA tensor [B, in_elems] of the plan dtype when the plan has batch-dependent input tables (soft
+        evidence likelihoods; layout in plan.inputs), else None.
         Returns out: [B, out_elems] CUDA tensor of the plan dtype. Asynchronous on the current stream."""
         torch = _torch()
+        in_elems = self.plan.in_elems
+        if in_elems and soft is None:
+            raise ValueError("this plan has soft-evidence input tables: pass `soft` [B, in_elems]")
+        if soft is not None:
+            if not in_elems:
+                raise ValueError("this plan has no soft-evidence input tables")
+            if soft.dtype != self.torch_dtype or not soft.is_cuda or not soft.is_contiguous() or soft.dim() != 2 or soft.shape[1] != in_elems:
+                raise ValueError(f"soft must be a contiguous {self.dtype_name} CUDA tensor [B, {in_elems}]")
+            if ev_states is not None and soft.shape[0] != ev_states.shape[0]:
+                raise ValueError("soft and ev_states disagree on the batch size")
         if workspace is None:
-            B_all = ev_states.shape[0] if ev_states is not None else (out.shape[0] if out is not None else 0)
+            B_all = ev_states.shape[0] if ev_states is not None else (out.shape[0] if out is not None else (soft.shape[0] if soft is not None else 0))
             if B_all > 32 and (self.workspace_bytes(B_all) > self.MAX_WORKSPACE_BYTES or B_all > self.MAX_ROWS_PER_PASS):
                 per_set = self.workspace_bytes(32) // 32
                 tile = max(32, int(self.MAX_WORKSPACE_BYTES // max(per_set, 1)) // 32 * 32)
@@ -136,12 +148,13 @@ class CompiledPlan:
                     out = torch.empty((B_all, self.out_elems), dtype=self.torch_dtype, device=self.device)
                 for lo in range(0, B_all, tile):
                     hi = min(B_all, lo + tile)
-                    self.run(None if ev_states is None else ev_states[lo:hi], out=out[lo:hi])
+                    self.run(None if ev_states is None else ev_states[lo:hi], out=out[lo:hi],
+                             soft=None if soft is None else soft[lo:hi])
                 return out
         if ev_states is None:
-            if out is None:
+            if out is None and soft is None:
                 raise ValueError("batch size unknown: pass ev_states or out")
-            B = out.shape[0]
+            B = out.shape[0] if out is not None else soft.shape[0]
         else:
             if ev_states.dtype != torch.int32 or not ev_states.is_cuda or not ev_states.is_contiguous():
                 raise ValueError("ev_states must be a contiguous int32 CUDA tensor")
@@ -164,9 +177,10 @@ class CompiledPlan:
                 raise ValueError(f"workspace too small: need {need} bytes")
             stream = torch.cuda.current_stream(self.device).cuda_stream
             N.check(
-                self.lib.pgx_run_batch(
+                self.lib.pgx_run_batch_soft(
                     self.handle,
                     C.c_void_p(ev_states.data_ptr() if (ev_states is not None and self.n_ev) else 0),
+                    C.c_void_p(soft.data_ptr() if soft is not None else 0),
                     C.c_void_p(out.data_ptr()),
                     C.c_void_p(workspace.data_ptr()),
                     workspace.numel() * workspace.element_size(),
@@ -275,9 +289,12 @@ class CompiledPlan:
                 st.synchronize()
         return out_pinned
 
-    def run_host(self, ev_states_np: np.ndarray) -> np.ndarray:
-        """Convenience: host int array [B, n_ev] -> host posteriors [B, out_elems] (range-checks the states)."""
+    def run_host(self, ev_states_np: np.ndarray, soft=None) -> np.ndarray:
+        """Convenience: host int array [B, n_ev] (+ host soft-evidence rows [B, in_elems]) -> host posteriors
+        [B, out_elems] (range-checks the states)."""
         torch = _torch()
+        if soft is not None:
+            soft = torch.from_numpy(np.ascontiguousarray(soft, dtype=np.float64)).to(self.device, dtype=self.torch_dtype)
         ev = np.ascontiguousarray(ev_states_np, dtype=np.int32).reshape(-1, max(self.n_ev, 1))
         cards = [self.plan.card[v] for v in self.plan.ev_vars]
         for j, c in enumerate(cards):
@@ -287,6 +304,6 @@ class CompiledPlan:
         if self.n_ev == 0:
             B = max(1, int(np.asarray(ev_states_np).shape[0])) if np.asarray(ev_states_np).ndim >= 1 else 1
             out = torch.empty((B, self.out_elems), dtype=self.torch_dtype, device=self.device)
-            return self.run(None, out=out).cpu().numpy()
+            return self.run(None, out=out, soft=soft).cpu().numpy()
         dev = torch.from_numpy(ev).to(self.device)
-        return self.run(dev).cpu().numpy()
+        return self.run(dev, soft=soft).cpu().numpy()

@@ -24,6 +24,41 @@ from .models import DiscreteBayesianNetwork, JunctionTree, from_pgmpy, junction_
 from . import planner as PL
 
 
+def _soft_items(inf, virtual_evidence):
+    """{variable: (state names or None, likelihoods [B or 1, card])} with the reference's argument checks
+    (pgmpy/inference/base.py:214-254)."""
+    items = {}
+    for item in virtual_evidence:
+        if isinstance(item, tuple) and len(item) == 2 and not hasattr(item, "variables"):
+            var, vals = item
+            vals = np.asarray(vals.detach().cpu().numpy() if hasattr(vals, "detach") else vals, dtype=np.float64)
+            vals = vals.reshape(1, -1) if vals.ndim == 1 else vals
+            names = None
+        else:
+            if not isinstance(item, (TabularCPD, DiscreteFactor)) and not hasattr(item, "variables"):
+                raise ValueError(
+                    f"Virtual evidence should be an instance of TabularCPD or DiscreteFactor. Got: {type(item)}"
+                )
+            if len(item.variables) > 1:
+                raise ValueError("Virtual evidence should be defined on individual variables.")
+            var = item.variables[0]
+            vals = np.asarray(item.values, dtype=np.float64).reshape(1, -1)
+            names = list(item.state_names[var]) if getattr(item, "state_names", None) else None
+        if var not in inf.variables:
+            raise ValueError("Evidence provided for variable which is not in the model")
+        if vals.ndim != 2 or vals.shape[1] != inf.cardinality[var]:
+            raise ValueError(
+                "The number of states/cardinality for the evidence should"
+                " be same as the number of states/cardinality of the variable in the model"
+            )
+        if names is not None and list(names) != list(inf.states[var]):
+            # the reference's child CPD carries the evidence's own state names for the parent; align by name
+            order = [names.index(s) for s in inf.states[var]]
+            vals = vals[:, order]
+        items[var] = (names, vals)
+    return items
+
+
 def _as_bn(model):
     if isinstance(model, (DiscreteBayesianNetwork, JunctionTree)):
         return model
@@ -94,12 +129,32 @@ class _Inference:
         card = [self.cardinality[v] for v in variables]
         return DiscreteFactor(list(variables), card, values, {v: self.states[v] for v in variables})
 
-    def _run(self, cp: CompiledPlan, ev_states):
+    def _soft_rows(self, cp: CompiledPlan, virtual_evidence, batch=None):
+        """Soft (virtual) evidence -> the plan's input rows [B, in_elems] on the device. `virtual_evidence`: a list of
+        TabularCPD / DiscreteFactor over one variable each (the reference's type, inference/base.py:256-299: one
+        likelihood vector, B = 1) or of (variable, array [B, card]) pairs (batched: one vector per evidence set)."""
+        torch = require_cuda()
+        items = _soft_items(self, virtual_evidence)
+        B = batch
+        for _, vals in items.values():
+            B = vals.shape[0] if B is None or vals.shape[0] != 1 else B
+        B = B or 1
+        rows = np.empty((B, cp.plan.in_elems), dtype=np.float64)
+        for vars_, size, off in cp.plan.inputs:
+            _, vals = items[vars_[0]]
+            if vals.shape[0] not in (1, B):
+                raise ValueError("soft evidence batch sizes disagree")
+            rows[:, off:off + size] = vals
+        return torch.from_numpy(rows).to(cp.device, dtype=cp.torch_dtype)
+
+    def _run(self, cp: CompiledPlan, ev_states, soft=None):
         torch = require_cuda()
         if cp.n_ev == 0:
             B = int(ev_states.shape[0]) if ev_states is not None and hasattr(ev_states, "shape") else 1
+            if soft is not None:
+                B = int(soft.shape[0])
             out = torch.empty((max(B, 1), cp.out_elems), dtype=cp.torch_dtype, device=cp.device)
-            return cp.run(None, out=out)
+            return cp.run(None, out=out, soft=soft)
         if isinstance(ev_states, np.ndarray) or not hasattr(ev_states, "is_cuda"):
             ev = np.ascontiguousarray(np.asarray(ev_states, dtype=np.int32)).reshape(-1, cp.n_ev)
             for j, v in enumerate(cp.plan.ev_vars):
@@ -108,7 +163,7 @@ class _Inference:
             ev_t = torch.from_numpy(ev).to(cp.device)
         else:
             ev_t = ev_states
-        return cp.run(ev_t)
+        return cp.run(ev_t, soft=soft)
 
     @staticmethod
     def _warn_nan(values):
@@ -148,21 +203,21 @@ class VariableElimination(_Inference):
             )
         return bn
 
-    def _plan(self, variables, ev_vars, joint, elimination_order, prune=True, reduce_max=False) -> CompiledPlan:
+    def _plan(self, variables, ev_vars, joint, elimination_order, prune=True, reduce_max=False, soft_vars=()) -> CompiledPlan:
         order_key = tuple(elimination_order) if isinstance(elimination_order, (list, tuple)) else None
-        key = ("ve", tuple(variables), tuple(ev_vars), joint, order_key, prune, reduce_max)
+        key = ("ve", tuple(variables), tuple(ev_vars), joint, order_key, prune, reduce_max, tuple(soft_vars))
         cp = self._plans.get(key)
         if cp is None:
             if isinstance(self.model, JunctionTree):
                 factors = [(tuple(f.variables), f.values, None) for f in self.model.get_factors()]
                 plan = PL.compile_factor_ve_plan(
                     factors, self.cardinality, variables, ev_vars, joint=joint, normalize=True,
-                    elimination_order=order_key, reduce_max=reduce_max,
+                    elimination_order=order_key, reduce_max=reduce_max, soft_vars=soft_vars,
                 )
             else:
                 plan = PL.compile_ve_plan(
                     self.model, variables, ev_vars, joint=joint, prune=prune, elimination_order=order_key,
-                    reduce_max=reduce_max,
+                    reduce_max=reduce_max, soft_vars=soft_vars,
                 )
             cp = self._compile(plan)
             self._plans[key] = cp
@@ -182,15 +237,18 @@ class VariableElimination(_Inference):
         `elimination_order`: heuristic names are accepted for compatibility — the engine always uses its
         own min-fill order (order changes results only at ~1e-16); an explicit list is honoured."""
         evidence = self._check_query(variables, evidence)
-        if virtual_evidence is not None and isinstance(self.model, DiscreteBayesianNetwork):
-            sub = VariableElimination(self._virtual(virtual_evidence), dtype=self.dtype)
-            virt = {"__" + str(c.variables[0]): 0 for c in virtual_evidence}
-            return sub.query(variables, {**evidence, **virt}, None, elimination_order, joint, show_progress)
         variables = list(variables)
         ev_vars = list(evidence)
-        cp = self._plan(variables, ev_vars, joint, elimination_order)
+        soft_vars, soft = (), None
+        if virtual_evidence is not None and isinstance(self.model, DiscreteBayesianNetwork):
+            # soft evidence is a per-evidence-set INPUT of the plan (one plan per signature, cached) — the factor the
+            # reference gets by adding an observed binary child per query (inference/base.py:256-299)
+            soft_vars = tuple(_soft_items(self, virtual_evidence))
+        cp = self._plan(variables, ev_vars, joint, elimination_order, soft_vars=soft_vars)
+        if soft_vars:
+            soft = self._soft_rows(cp, virtual_evidence)
         states = self._states_of(ev_vars, [evidence])  # KeyError on unknown state names
-        out = self._run(cp, states).cpu().numpy()[0]
+        out = self._run(cp, states, soft).cpu().numpy()[0]
         self._warn_nan(out)
         if joint:
             shape = [self.cardinality[v] for v in variables]
@@ -201,13 +259,18 @@ class VariableElimination(_Inference):
             res[v] = self._to_factor([v], out[seg.out_offset : seg.out_offset + seg.table.size])
         return res
 
-    def query_batch(self, variables, evidence_vars, evidence_states, joint=True, elimination_order=None):
+    def query_batch(self, variables, evidence_vars, evidence_states, joint=True, elimination_order=None,
+                    virtual_evidence=None):
         """One signature, B evidence sets. evidence_states: int32 [B, k] state INDICES (host array or CUDA
-        tensor) in `evidence_vars` order. Returns a CUDA tensor [B, out_elems]: the joint over `variables`
-        (row-major in the given order) or the concatenated per-variable marginals when joint=False."""
+        tensor) in `evidence_vars` order. `virtual_evidence`: [(variable, likelihoods [B, card]), ...] — soft evidence
+        that differs per evidence set (semantics of inference/base.py:256-299 per row).
+        Returns a CUDA tensor [B, out_elems]: the joint over `variables` (row-major in the given order) or the
+        concatenated per-variable marginals when joint=False."""
         self._check_query(variables, {v: None for v in evidence_vars})
-        cp = self._plan(list(variables), list(evidence_vars), joint, elimination_order)
-        return self._run(cp, evidence_states)
+        soft_vars = tuple(_soft_items(self, virtual_evidence)) if virtual_evidence else ()
+        cp = self._plan(list(variables), list(evidence_vars), joint, elimination_order, soft_vars=soft_vars)
+        B = int(np.shape(evidence_states)[0]) if len(evidence_vars) else None
+        return self._run(cp, evidence_states, self._soft_rows(cp, virtual_evidence, B) if soft_vars else None)
 
     def marginals_plan(self, evidence_vars, variables=None) -> CompiledPlan:
         """One plan holding the VE-mode posterior of every unobserved variable (or of `variables`), each with its own
@@ -408,11 +471,11 @@ class BeliefPropagation(_Inference):
     def get_sepset_beliefs(self):
         return self.sepset_beliefs
 
-    def _jt_plan(self, ev_vars, variables=None, emit_beliefs=False) -> CompiledPlan:
-        key = ("jt", tuple(ev_vars), None if variables is None else tuple(variables), emit_beliefs)
+    def _jt_plan(self, ev_vars, variables=None, emit_beliefs=False, soft_vars=()) -> CompiledPlan:
+        key = ("jt", tuple(ev_vars), None if variables is None else tuple(variables), emit_beliefs, tuple(soft_vars))
         cp = self._plans.get(key)
         if cp is None:
-            plan = PL.compile_jt_plan(self._jt, ev_vars, variables, emit_beliefs=emit_beliefs)
+            plan = PL.compile_jt_plan(self._jt, ev_vars, variables, emit_beliefs=emit_beliefs, soft_vars=soft_vars)
             cp = self._compile(plan)
             self._plans[key] = cp
         return cp
@@ -452,31 +515,30 @@ class BeliefPropagation(_Inference):
         variables come from the junction-tree plan, joints over several variables from an un-pruned
         elimination plan (the reference's out-of-clique query, :1047-1111, computes the same function)."""
         evidence = self._check_query(variables, evidence)
-        if virtual_evidence is not None and isinstance(self.model, DiscreteBayesianNetwork):
-            ve = VariableElimination(self.model, dtype=self.dtype)
-            sub = BeliefPropagation(ve._virtual(virtual_evidence), dtype=self.dtype)
-            virt = {"__" + str(c.variables[0]): 0 for c in virtual_evidence}
-            return sub.query(variables, {**evidence, **virt}, None, joint, show_progress)
         variables = list(variables)
         ev_vars = list(evidence)
         states = self._states_of(ev_vars, [evidence])
+        soft_vars = ()
+        if virtual_evidence is not None and isinstance(self.model, DiscreteBayesianNetwork):
+            soft_vars = tuple(_soft_items(self, virtual_evidence))  # likelihood vectors = input tables of the plan
         if len(variables) == 1 or not joint:
-            cp = self._jt_plan(ev_vars, variables)
-            out = self._run(cp, states).cpu().numpy()[0]
+            cp = self._jt_plan(ev_vars, variables, soft_vars=soft_vars)
+            out = self._run(cp, states, self._soft_rows(cp, virtual_evidence) if soft_vars else None).cpu().numpy()[0]
             self._warn_nan(out)
             res = {}
             for seg in cp.plan.segments:
                 v = seg.vars[0]
                 res[v] = self._to_factor([v], out[seg.out_offset : seg.out_offset + seg.table.size])
             return res[variables[0]] if joint else res
-        key = ("bp-joint", tuple(variables), tuple(ev_vars))
+        key = ("bp-joint", tuple(variables), tuple(ev_vars), soft_vars)
         cp = self._plans.get(key)
         if cp is None:
             factors = [(c, p, None) for c, p in zip(self._jt.cliques, self._jt.potentials)]
-            plan = PL.compile_factor_ve_plan(factors, self.cardinality, variables, ev_vars, joint=True, normalize=True)
+            plan = PL.compile_factor_ve_plan(factors, self.cardinality, variables, ev_vars, joint=True, normalize=True,
+                                             soft_vars=soft_vars)
             cp = self._compile(plan)
             self._plans[key] = cp
-        out = self._run(cp, states).cpu().numpy()[0]
+        out = self._run(cp, states, self._soft_rows(cp, virtual_evidence) if soft_vars else None).cpu().numpy()[0]
         self._warn_nan(out)
         return self._to_factor(variables, out.reshape([self.cardinality[v] for v in variables]))
 
@@ -505,13 +567,16 @@ class BeliefPropagation(_Inference):
         idx = int(VariableElimination._argmax_rows(self, t)[0].item())
         return VariableElimination._decode(self, list(variables), idx)
 
-    def marginals_plan(self, evidence_vars, variables=None) -> CompiledPlan:
+    def marginals_plan(self, evidence_vars, variables=None, soft_vars=()) -> CompiledPlan:
         """Compiled all-marginals plan for one evidence-variable signature (bench / batched callers)."""
         self._check_query(variables or [], {v: None for v in evidence_vars}, allow_empty=True)
-        return self._jt_plan(list(evidence_vars), variables)
+        return self._jt_plan(list(evidence_vars), variables, soft_vars=tuple(soft_vars))
 
-    def marginals_batch(self, evidence_vars, evidence_states, variables=None):
+    def marginals_batch(self, evidence_vars, evidence_states, variables=None, virtual_evidence=None):
         """Posterior marginals of every unobserved variable (or `variables`) for B evidence sets:
-        CUDA tensor [B, sum card]; column layout in `marginals_plan(...).plan.segments`."""
-        cp = self.marginals_plan(evidence_vars, variables)
-        return self._run(cp, evidence_states)
+        CUDA tensor [B, sum card]; column layout in `marginals_plan(...).plan.segments`.
+        `virtual_evidence`: [(variable, likelihoods [B, card]), ...] — per-evidence-set soft evidence."""
+        soft_vars = tuple(_soft_items(self, virtual_evidence)) if virtual_evidence else ()
+        cp = self.marginals_plan(evidence_vars, variables, soft_vars)
+        B = int(np.shape(evidence_states)[0]) if len(evidence_vars) else None
+        return self._run(cp, evidence_states, self._soft_rows(cp, virtual_evidence, B) if soft_vars else None)

@@ -21,7 +21,8 @@ Every step is the same operation, a fused product + sum-out over a batch of evid
 
 Word pool layout (int32 words; 64-bit values as lo,hi):
   header[16]: 0 magic 'PGX1' | 1 version | 2 n_ev | 3 n_steps | 4 n_segs | 5 out_elems | 6,7 ws_entries
-              | 8,9 const_entries | 10 step_index_off | 11 segs_off | 12 max_ops | 13 max_axes | 14 ev_card_off | 15 0
+              | 8,9 const_entries | 10 step_index_off | 11 segs_off | 12 max_ops | 13 max_axes | 14 ev_card_off
+              | 15 inputs_off (0: the plan has no batch-dependent input tables)
   ev_card[n_ev]: cardinality of each evidence slot (states are range-checked against it)
   step_index[n_steps]: word offset of each step record
   step record: 0 A (#out axes) | 1 S (#sum axes) | 2 K (#operands) | 3 flags (bit0 max-reduce, bit1 has divisor)
@@ -31,6 +32,10 @@ Word pool layout (int32 words; 64-bit values as lo,hi):
                | 4 ev_off (words from step start) | 5 0 | strides over out axes[A] | strides over sum axes[S]
   evidence pair: (slot, stride)
   segment record[8]: 0,1 work offset | 2 size | 3 out offset | 4 flags (bit0 normalise) | 5,6,7 0
+  inputs block (at inputs_off): n_inputs | in_elems | n_inputs x (0,1 work offset | 2 size | 3 offset in the input row)
+      Batch-dependent INPUT tables: work tables the caller fills per evidence set (soft / virtual evidence: one
+      likelihood vector per variable, the factor pgmpy/inference/base.py:256-299 adds as an observed binary child).
+      The engine copies row b of the caller's `soft[B, in_elems]` into them before the first step.
 """
 from __future__ import annotations
 
@@ -78,6 +83,7 @@ class Table:
     tid: int = -1
     first_step: int = -1
     last_step: int = -1
+    is_input: bool = False  # work table filled from the caller's per-evidence-set input row before the first step
 
     @property
     def size(self) -> int:
@@ -116,6 +122,8 @@ class Plan:
     card: Dict[Hashable, int]
     steps: List[StepSpec] = field(default_factory=list, repr=False)
     meta: dict = field(default_factory=dict)
+    inputs: List[Tuple[Tuple[Hashable, ...], int, int]] = field(default_factory=list)  # (vars, size, offset in the input row)
+    in_elems: int = 0
 
     def algorithmic_bytes(self, batch: int, itemsize: int = 8) -> int:
         """every tensor counted once per step in which it is an operand or result,
@@ -132,7 +140,7 @@ class Plan:
                 else:
                     const += t.size
             total += itemsize * (batch * work + const)
-        total += 4 * batch * len(self.ev_vars) + itemsize * batch * self.out_elems
+        total += 4 * batch * len(self.ev_vars) + itemsize * batch * (self.out_elems + 2 * self.in_elems)
         return total
 
     # ---- plan cache on disk: a compiled plan is two arrays + a little metadata -----------
@@ -148,6 +156,7 @@ class Plan:
             "segments": segs, "out_elems": self.out_elems, "ws_entries": self.ws_entries, "n_steps": self.n_steps,
             "meta": {k: v for k, v in self.meta.items() if isinstance(v, (str, int, float, bool))},
             "alg_bytes_per_set": self.algorithmic_bytes(1) if self.steps else self.meta.get("alg_bytes_per_set", 0),
+            "inputs": [[list(map(str, v)), int(n), int(o)] for v, n, o in self.inputs], "in_elems": int(self.in_elems),
         }
         np.savez_compressed(path, pool=self.pool, const_blob=self.const_blob, header=np.array(json.dumps(header)))
 
@@ -167,7 +176,8 @@ class Plan:
         meta["alg_bytes_per_set"] = header["alg_bytes_per_set"]
         return cls(pool=pool, const_blob=blob, ev_vars=tuple(header["ev_vars"]), segments=segments,
                    out_elems=header["out_elems"], ws_entries=header["ws_entries"], n_steps=header["n_steps"],
-                   card=header["card"], steps=[], meta=meta)
+                   card=header["card"], steps=[], meta=meta,
+                   inputs=[(tuple(v), n, o) for v, n, o in header.get("inputs", [])], in_elems=header.get("in_elems", 0))
 
     def operand_loads(self) -> int:
         """Operand loads (= multiplies) per evidence set: sum over steps of |out| * |sum| * #operands."""
@@ -204,6 +214,7 @@ class PlanBuilder:
         self._const_len = 0
         self._const_cache: Dict[int, Table] = {}
         self._memo: Dict[tuple, Table] = {}  # contraction -> its result table (common-subexpression reuse)
+        self.inputs: List[Table] = []
 
     # ---- tables ----------------------------------------------------------------------------
     def add_const(self, vars_: Sequence[Hashable], values: np.ndarray, key=None) -> Table:
@@ -233,6 +244,14 @@ class PlanBuilder:
                 raise ValueError(f"work table scope may not contain evidence variable {v}")
         t = Table(KIND_WORK, vars_, tuple(self.card[v] for v in vars_), tid=len(self.tables))
         self.tables.append(t)
+        return t
+
+    def add_input(self, vars_: Sequence[Hashable]) -> Table:
+        """A batch-dependent table the CALLER supplies per evidence set (soft evidence likelihoods). It is a work
+        table that is alive from before the first step; its values arrive as a slice of the input row."""
+        t = self.new_work(vars_)
+        t.is_input = True
+        self.inputs.append(t)
         return t
 
     # ---- steps -----------------------------------------------------------------------------
@@ -383,11 +402,11 @@ class PlanBuilder:
     def mark(self):
         """Snapshot for rollback(): lets the planner build a candidate step sequence, price it, and undo it."""
         return (len(self.tables), len(self.steps), len(self.segments), len(self._const_chunks), self._const_len,
-                dict(self._const_cache), dict(self._memo), [t.last_step for t in self.tables])
+                dict(self._const_cache), dict(self._memo), [t.last_step for t in self.tables], len(self.inputs))
 
     def rollback(self, mk) -> None:
-        n_t, n_s, n_g, n_c, c_len, c_cache, memo, last = mk
-        del self.tables[n_t:], self.steps[n_s:], self.segments[n_g:], self._const_chunks[n_c:]
+        n_t, n_s, n_g, n_c, c_len, c_cache, memo, last, n_in = mk
+        del self.tables[n_t:], self.steps[n_s:], self.segments[n_g:], self._const_chunks[n_c:], self.inputs[n_in:]
         self._const_len = c_len
         self._const_cache = dict(c_cache)  # copies: the same mark may be rolled back to more than once
         self._memo = dict(memo)
@@ -495,7 +514,7 @@ class PlanBuilder:
         for i, st in enumerate(self.steps):
             lv = 0
             for t, _ in st.operands:
-                if t.kind == KIND_WORK:
+                if t.kind == KIND_WORK and not t.is_input:
                     lv = max(lv, level[producer[t.tid]] + 1)
             level[i] = lv
             st.level = lv
@@ -505,7 +524,7 @@ class PlanBuilder:
         # 2. liveness in units of levels: a table is born at its producer's level and dies after the last
         #    level that reads it (emitted tables never die)
         for t in self.tables:
-            t.first_step = -1
+            t.first_step = 0 if t.is_input else -1  # inputs are written before level 0 runs
             if t.last_step < (1 << 59):
                 t.last_step = -1
         for st in self.steps:
@@ -517,7 +536,7 @@ class PlanBuilder:
         for t in work:
             if t.last_step < 0:
                 t.last_step = t.first_step
-        by_birth = sorted(work, key=lambda t: (t.first_step, t.tid))
+        by_birth = sorted(work, key=lambda t: (t.first_step, not t.is_input, t.tid))
         free: List[Tuple[int, int]] = []  # (offset, size), kept sorted by offset
         live: List[Table] = []
         top = 0
@@ -583,12 +602,21 @@ class PlanBuilder:
             index.append(pos)
             pos += len(r)
         segs_off = pos
-        header += [step_index_off, segs_off, max_ops, max_axes, ev_card_off, 0]
+        inputs_off = segs_off + SEG_WORDS * len(self.segments) if self.inputs else 0
+        header += [step_index_off, segs_off, max_ops, max_axes, ev_card_off, inputs_off]
         words = header + [self.card[v] for v in self.ev_vars] + index
         for r in step_recs:
             words += r
         for s in self.segments:
             words += [*_lohi(s.table.offset), s.table.size, s.out_offset, SEG_NORMALIZE if s.normalize else 0, 0, 0, 0]
+        in_elems = 0
+        plan_inputs = []
+        if self.inputs:
+            words += [len(self.inputs), sum(t.size for t in self.inputs)]
+            for t in self.inputs:
+                words += [*_lohi(t.offset), t.size, in_elems]
+                plan_inputs.append((t.vars, t.size, in_elems))
+                in_elems += t.size
         pool = np.array(words, dtype=np.int64)
         if pool.max(initial=0) >= (1 << 31) or pool.min(initial=0) < -(1 << 31):
             raise ValueError("plan word does not fit int32")
@@ -604,4 +632,6 @@ class PlanBuilder:
             card=dict(self.card),
             steps=list(self.steps),
             meta=dict(meta or {}),
+            inputs=plan_inputs,
+            in_elems=in_elems,
         )

@@ -118,12 +118,22 @@ def build_junction_tree(model: DiscreteBayesianNetwork) -> JunctionTree:
 # ---------------------------------------------------------------------------------------------
 # VE plans
 # ---------------------------------------------------------------------------------------------
-def _pruned_factors(model: DiscreteBayesianNetwork, variables, evidence_vars, prune: bool):
+def _pruned_factors(model: DiscreteBayesianNetwork, variables, evidence_vars, prune: bool, soft_vars=()):
+    """`soft_vars`: variables carrying soft (virtual) evidence. The reference gives each an observed binary child
+    (pgmpy/inference/base.py:256-299) BEFORE it prunes, so for the kept set they count as parents of evidence."""
     nodes = model.nodes()
     if prune:
-        parents = {n: model.get_parents(n) for n in nodes}
-        children = {n: model.get_children(n) for n in nodes}
-        kept = G.prune_nodes(parents, children, list(variables), list(evidence_vars))
+        parents = {n: list(model.get_parents(n)) for n in nodes}
+        children = {n: list(model.get_children(n)) for n in nodes}
+        virt = []
+        for v in soft_vars:
+            node = ("__soft__", v)
+            parents[node] = [v]
+            children[node] = []
+            children[v] = children[v] + [node]
+            virt.append(node)
+        kept = G.prune_nodes(parents, children, list(variables), list(evidence_vars) + virt)
+        kept = set(kept) - set(virt)
     else:
         kept = set(nodes)
     factors = []
@@ -152,6 +162,7 @@ def compile_factor_ve_plan(
     meta: Optional[dict] = None,
     reduce_max: bool = False,
     builder: Optional[PlanBuilder] = None,
+    soft_vars: Sequence[Hashable] = (),
 ) -> Plan:
     """Sum-product variable elimination over an explicit factor list.
 
@@ -168,6 +179,12 @@ def compile_factor_ve_plan(
         if all(v in evset for v in scope):
             continue
         work.append(b.add_const(scope, vals, key=key if builder is not None else None))
+    for v in soft_vars:
+        # soft evidence = one more factor over v whose values arrive per evidence set (the reduced CPD of the observed
+        # binary child the reference adds, inference/base.py:256-299)
+        if v in evset:
+            raise ValueError(f"soft evidence on the observed variable {v}")
+        work.append(b.add_input([v]))
     free_scopes = [[v for v in t.vars if v not in evset] for t in work]
     present = set(v for sc in free_scopes for v in sc)
     for q in variables:
@@ -210,7 +227,7 @@ def compile_factor_ve_plan(
                 m = b.contract([joint_t], [q], level=level + 1)
                 b.emit(m, normalize, [q])
     m = {"mode": "ve-max" if reduce_max else "ve", "variables": tuple(variables), "evidence_vars": tuple(ev), "joint": joint,
-         "order": tuple(order)}
+         "order": tuple(order), "soft_vars": tuple(soft_vars)}
     m.update(meta or {})
     if builder is not None:
         return m  # the caller finalizes the shared builder
@@ -225,10 +242,12 @@ def compile_ve_plan(
     prune: bool = True,
     elimination_order: Optional[Sequence[Hashable]] = None,
     reduce_max: bool = False,
+    soft_vars: Sequence[Hashable] = (),
 ) -> Plan:
     """reduce_max=True eliminates with max instead of sum (DiscreteFactor.maximize): the table the reference's
-    max_marginal takes its maximum of (ExactInference.py:459-526)."""
-    kept, factors = _pruned_factors(model, variables, evidence_vars, prune)
+    max_marginal takes its maximum of (ExactInference.py:459-526). `soft_vars`: variables with soft (virtual)
+    evidence; their likelihood vectors are input tables of the plan (Plan.inputs), one row per evidence set."""
+    kept, factors = _pruned_factors(model, variables, evidence_vars, prune, soft_vars)
     ev = [v for v in evidence_vars]  # all evidence variables survive pruning (base.py:192-194)
     rank = {v: i for i, v in enumerate(model.nodes())}
     return compile_factor_ve_plan(
@@ -242,6 +261,7 @@ def compile_ve_plan(
         rank=rank,
         meta={"kept": tuple(sorted(kept, key=lambda v: rank[v])), "prune": prune},
         reduce_max=reduce_max,
+        soft_vars=soft_vars,
     )
 
 
@@ -403,6 +423,7 @@ def compile_jt_plan(
     distribute: str = "auto",
     reduce_max: bool = False,
     factorized="auto",
+    soft_vars: Sequence[Hashable] = (),
 ) -> Plan:
     """Two-pass message passing on the rooted junction tree for one evidence-variable signature.
 
@@ -439,7 +460,7 @@ def compile_jt_plan(
                     continue
                 if d == "ss" and hub and distribute == "auto":
                     continue
-                cands.append(compile_jt_plan(jt, evidence_vars, variables, normalize, False, d, reduce_max, f))
+                cands.append(compile_jt_plan(jt, evidence_vars, variables, normalize, False, d, reduce_max, f, soft_vars))
         cost = [plan_cost(p) for p in cands]
         best = min(range(len(cands)), key=lambda i: cost[i])
         # stay with the (dense, Shafer-Shenoy) candidate — smallest workspace, every step on the fused kernel's fast
@@ -464,6 +485,16 @@ def compile_jt_plan(
             psi.append(mine)
     else:
         psi = [[b.add_const(jt.cliques[i], jt.potentials[i])] for i in range(n)]
+    for v in soft_vars:
+        # soft evidence: a per-evidence-set likelihood vector over v (Plan.inputs) joins the potential of the smallest
+        # clique holding v — the reference's observed binary child of v (inference/base.py:256-299) after reduction
+        if v in evset:
+            raise ValueError(f"soft evidence on the observed variable {v}")
+        home = [i for i in range(n) if v in jt.cliques[i]]
+        if not home:
+            raise ValueError(f"soft-evidence variable {v} is not in the junction tree")
+        i = min(home, key=lambda i: (int(np.prod([card[u] for u in free[i]], dtype=np.int64)), i))
+        psi[i] = psi[i] + [b.add_input([v])]
     ones: Dict[Hashable, Table] = {}
 
     def covered(ops, need):

@@ -737,3 +737,59 @@ def test_wide_operand_steps_without_reassociation(torch_cuda, monkeypatch):
         cp = _engine()(plan)
         cp.set_mode(mode, 0, kernel, step_kernel)
         assert rel_err(cp.run_host(states), want) <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["alarm", "child"])
+def test_batched_soft_evidence_vs_reference_golden(torch_cuda, name):
+    """soft (virtual) evidence as a batch-dependent [B, card] multiplier. Every golden case
+    (posteriors of the unmodified reference under virtual_evidence=[TabularCPD, TabularCPD], oracle/make_golden_virtual.py)
+    through the batched API with a different likelihood row per evidence set, VE mode and BP mode, fixed 1e-12; every
+    execution variant of the engine on the all-marginals plan; the reference-typed single query."""
+    import json
+    import os
+
+    from pgmpy_b200 import TabularCPD
+    from pgmpy_b200.inference import BeliefPropagation, VariableElimination
+
+    torch = torch_cuda
+    with open(os.path.join(os.path.dirname(__file__), "golden", f"ref_{name}_virtual.json")) as f:
+        g = json.load(f)
+    m = px.get_example_model(name)
+    ve, bp = VariableElimination(m), BeliefPropagation(m)
+    ev_vars = g["ev_vars"]
+    states = np.asarray(g["ev_states"], dtype=np.int32)
+    for c in g["cases"]:
+        like = [np.asarray(l, dtype=np.float64) for l in c["likelihoods"]]
+        # batch of 3: uniform likelihoods / the golden row / another row
+        virt = [(v, np.stack([np.ones_like(l), l, l[::-1] * 0.5 + 0.1])) for v, l in zip(c["soft_vars"], like)]
+        ev3 = np.stack([states[c["case"]]] * 3)
+        got = ve.query_batch([c["query"]], ev_vars, ev3, virtual_evidence=virt).cpu().numpy()
+        assert rel_err(got[1], np.asarray(c["ve"])) <= 1e-12
+        plain = ve.query_batch([c["query"]], ev_vars, ev3[:1]).cpu().numpy()
+        # (uniform likelihoods: same function, but the soft variables still change the reference's pruning)
+        assert rel_err(got[0], plain[0]) <= 1e-6
+        got = bp.marginals_batch(ev_vars, ev3, variables=[c["query"]], virtual_evidence=virt).cpu().numpy()
+        assert rel_err(got[1], np.asarray(c["bp"])) <= 1e-12
+    # the reference's own argument type, one query
+    c = g["cases"][0]
+    ev = {v: m.states[v][int(s)] for v, s in zip(ev_vars, states[c["case"]])}
+    cpds = [TabularCPD(v, len(l), np.asarray(l).reshape(-1, 1), state_names={v: list(m.states[v])})
+            for v, l in zip(c["soft_vars"], c["likelihoods"])]
+    np.testing.assert_allclose(ve.query([c["query"]], evidence=ev, virtual_evidence=cpds).values, c["ve"], rtol=1e-12)
+    np.testing.assert_allclose(bp.query([c["query"]], evidence=ev, virtual_evidence=cpds).values, c["bp"], rtol=1e-12)
+    # all-marginals plan with soft inputs: every execution variant against the numpy plan interpreter
+    soft_vars = c["soft_vars"]
+    B = 70
+    ev_b = np.stack([states[i % len(states)] for i in range(B)])
+    rng = np.random.default_rng(5)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, soft_vars=soft_vars)
+    soft = rng.uniform(0.05, 1.0, size=(B, plan.in_elems))
+    want = run_plan(plan.pool, plan.const_blob, ev_b, soft=soft)
+    for mode, kernel, step_kernel in EXEC_VARIANTS:
+        cp = _engine()(plan)
+        cp.set_mode(mode, 0, kernel, step_kernel)
+        assert rel_err(cp.run_host(ev_b, soft=soft), want) <= 1e-12, (mode, kernel, step_kernel)
+    cp32 = _engine()(plan, dtype="float32")
+    assert rel_err(cp32.run_host(ev_b, soft=soft), want) <= 1e-5
+    with pytest.raises(ValueError):
+        cp.run(torch.from_numpy(ev_b).cuda())  # the plan has input tables: `soft` is required

@@ -245,3 +245,66 @@ def test_plan_save_load_round_trip(tmp_path):
     assert [(s.vars, s.out_offset, s.table.size) for s in back.segments] == [(tuple(map(str, s.vars)), s.out_offset, s.table.size) for s in plan.segments]
     np.testing.assert_array_equal(run_plan(back.pool, back.const_blob, states), run_plan(plan.pool, plan.const_blob, states))
     np.testing.assert_array_equal(hostsim_run(back, states), hostsim_run(plan, states))
+
+
+def _load_virtual_golden(name):
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", f"ref_{name}_virtual.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", ["alarm", "child"])
+def test_soft_evidence_plans_match_reference_golden(name):
+    """Soft (virtual) evidence as per-evidence-set INPUT tables of the plan against posteriors
+    the unmodified reference produced with virtual_evidence=[TabularCPD...] (oracle/make_golden_virtual.py): VE mode
+    (its pruning sees the soft variables as parents of evidence, inference/base.py:256-299 then :154-212) and BP mode
+    (junction-tree plan, dense and factorized potentials), fixed 1e-12. Cases that share a signature run as ONE batch
+    with a different likelihood row per evidence set."""
+    g = _load_virtual_golden(name)
+    m = px.get_example_model(name)
+    jt = JTStructure.from_model(m)
+    ev_vars = g["ev_vars"]
+    states = np.asarray(g["ev_states"], dtype=np.int32)
+    for c in g["cases"]:
+        soft_vars, q = c["soft_vars"], c["query"]
+        row = np.concatenate([np.asarray(l, dtype=np.float64) for l in c["likelihoods"]])
+        ve = compile_ve_plan(m, [q], ev_vars, soft_vars=soft_vars)
+        assert [v[0] for v, _, _ in ve.inputs] == list(soft_vars) and ve.in_elems == row.size
+        # a batch of three evidence sets with three different likelihood rows: row 1 carries the golden case
+        soft = np.stack([np.ones_like(row), row, row[::-1] * 0.5 + 0.1])
+        ev3 = np.stack([states[(c["case"] + 1) % len(states)], states[c["case"]], states[c["case"]]])
+        got = run_plan(ve.pool, ve.const_blob, ev3, soft=soft)
+        assert rel_err(got[1], np.asarray(c["ve"])) <= 1e-12
+        for factorized in (False, True):
+            bp = compile_jt_plan(jt, ev_vars, [q], soft_vars=soft_vars, factorized=factorized, distribute="ss")
+            got = run_plan(bp.pool, bp.const_blob, ev3, soft=soft)
+            assert rel_err(got[1], np.asarray(c["bp"])) <= 1e-12
+        # uniform likelihoods change nothing: row 0 equals the plain BP-mode plan on that evidence set
+        plain = compile_jt_plan(jt, ev_vars, [q], distribute="ss", factorized=False)
+        assert rel_err(got[0], run_plan(plain.pool, plain.const_blob, ev3[:1])[0]) <= 1e-12
+    with pytest.raises(ValueError):
+        compile_ve_plan(m, [g["cases"][0]["query"]], ev_vars, soft_vars=[ev_vars[0]])
+
+
+def test_soft_evidence_all_marginals_plan_and_save_load(tmp_path):
+    """All-marginals junction-tree plan with two soft-evidence inputs: the auto-selected plan variant equals the dense
+    Shafer-Shenoy one, and the inputs block survives the plan cache."""
+    from pgmpy_b200.plan import Plan
+
+    m = px.get_example_model("alarm")
+    jt = JTStructure.from_model(m)
+    ev_vars, states = sample_evidence(m, 6, 5, seed=3)
+    soft_vars = [v for v in sorted(m.nodes()) if v not in ev_vars][:2]
+    rng = np.random.default_rng(1)
+    soft = rng.uniform(0.1, 1.0, size=(6, sum(m.get_cardinality()[v] for v in soft_vars)))
+    a = compile_jt_plan(jt, ev_vars, soft_vars=soft_vars)
+    b = compile_jt_plan(jt, ev_vars, soft_vars=soft_vars, distribute="ss", factorized=False)
+    want = run_plan(b.pool, b.const_blob, states, soft=soft)
+    assert rel_err(run_plan(a.pool, a.const_blob, states, soft=soft), want) <= 1e-12
+    path = str(tmp_path / "plan.npz")
+    a.save(path)
+    z = Plan.load(path)
+    assert z.in_elems == a.in_elems and [tuple(v) for v, _, _ in z.inputs] == [tuple(v) for v, _, _ in a.inputs]
+    assert rel_err(run_plan(z.pool, z.const_blob, states, soft=soft), want) <= 1e-12

@@ -1,2 +1,2 @@
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo rc=$?; tail -c 600 gpurun_out/bench_n1.err
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo rc=$?; tail -c 400 gpurun_out/bench_n1.err
