@@ -125,6 +125,17 @@ int pgx_run_batch(pgx_plan* plan, const int32_t* ev_states, void* out, void* wor
 int pgx_run_batch_soft(pgx_plan* plan, const int32_t* ev_states, const void* soft, void* out, void* workspace,
                        size_t workspace_bytes, int64_t B, void* stream);
 
+/* Max-product with back-pointers (most probable explanation over all unobserved variables; the reference maximises the
+ * full joint table, pgmpy/inference/ExactInference.py:609-612, :1222-1317). pgx_plan_set_trace attaches the traceback
+ * descriptor of a max-product junction-tree plan (HOST int32 words, layout in pgmpy_b200/planner.py
+ * compile_jt_mpe_plan: per clique, root first, the table of its upward belief and which of its axes are assigned
+ * there); pgx_run_batch_mpe runs the plan's steps and then the traceback kernel:
+ *   assign     DEVICE int32 [B, n_columns]  state index of every unobserved variable (column order of the descriptor)
+ * `soft` as in pgx_run_batch_soft (NULL when the plan has no input tables). */
+int pgx_plan_set_trace(pgx_plan* plan, const int32_t* trace, int64_t n_words);
+int pgx_run_batch_mpe(pgx_plan* plan, const int32_t* ev_states, const void* soft, int32_t* assign, void* workspace,
+                      size_t workspace_bytes, int64_t B, void* stream);
+
 /* Tracing aid: runs the plan in stepwise mode with a CUDA event after every step and returns the per-step device
  * time in milliseconds (step_ms[n_steps], n_steps >= the plan's step count). Synchronises the stream. */
 int pgx_profile_steps(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,

@@ -126,3 +126,28 @@ def run_plan(pool, const_blob, ev_states, dtype=np.float64, return_workspace=Fal
     if return_workspace:
         return out, ws
     return out
+
+
+def mpe_traceback(trace, ws):
+    """numpy restatement of k_mpe_traceback: walks the descriptor compile_jt_mpe_plan returns over the workspace of
+    run_plan(..., return_workspace=True) and returns the argmax assignment, int [B, n_columns]."""
+    trace = np.asarray(trace, dtype=np.int64)
+    n_cliques, n_cols = int(trace[0]), int(trace[1])
+    B = ws.shape[1]
+    assign = np.zeros((B, n_cols), dtype=np.int64)
+    at = 2
+    for _ in range(n_cliques):
+        off = P.lohi_to_int(trace[at], trace[at + 1])
+        n_ax = int(trace[at + 2])
+        axes = trace[at + 3 : at + 3 + 4 * n_ax].reshape(n_ax, 4)
+        at += 3 + 4 * n_ax
+        new = [a for a in axes if a[3]]
+        dims = [int(a[1]) for a in new]
+        rel = _grid(dims, [int(a[2]) for a in new])  # C-order over the axes assigned here
+        for b in range(B):
+            base = off + sum(int(assign[b, a[0]]) * int(a[2]) for a in axes if not a[3])
+            vals = ws[base + rel, b]
+            k = int(np.argmax(vals))  # first maximum
+            for a, d in zip(new, np.unravel_index(k, dims) if dims else ()):
+                assign[b, a[0]] = d
+    return assign

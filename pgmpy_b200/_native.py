@@ -24,6 +24,8 @@ EXPORTS = (
     "pgx_workspace_bytes",
     "pgx_run_batch",
     "pgx_run_batch_soft",
+    "pgx_plan_set_trace",
+    "pgx_run_batch_mpe",
     "pgx_profile_steps",
     "pgx_profile_launches",
     "pgx_stage_pick",
@@ -81,6 +83,10 @@ def load():
     lib.pgx_run_batch.restype = C.c_int
     lib.pgx_run_batch_soft.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p]
     lib.pgx_run_batch_soft.restype = C.c_int
+    lib.pgx_plan_set_trace.argtypes = [C.c_void_p, i32p, C.c_int64]
+    lib.pgx_plan_set_trace.restype = C.c_int
+    lib.pgx_run_batch_mpe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p]
+    lib.pgx_run_batch_mpe.restype = C.c_int
     lib.pgx_profile_steps.argtypes = [
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p, C.POINTER(C.c_float), C.c_int32,
     ]

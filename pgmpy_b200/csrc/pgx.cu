@@ -560,6 +560,59 @@ __global__ void __launch_bounds__(256) k_scatter_inputs(const int32_t* __restric
     }
 }
 
+// Max-product traceback (most probable explanation). The plan left one "upward belief" beta_i per clique in the
+// workspace (compile_jt_mpe_plan); walking the cliques root first, the variables of clique i that no ancestor fixed take
+// the argmax of beta_i restricted to the ones already fixed (first maximum in C-order, like numpy.argmax over the joint,
+// pgmpy/inference/ExactInference.py:609-612). Thread = evidence set: the restriction differs per evidence set, so the
+// reads are gathers; cliques are small next to the message passing that built them.
+//   trace: n_cliques | n_columns | per clique: work offset lo, hi | n_axes | n_axes x (column, card, stride, is_new)
+template <typename T>
+__global__ void __launch_bounds__(128) k_mpe_traceback(const int32_t* __restrict__ trace, const T* __restrict__ ws,
+                                                       int32_t* __restrict__ assign, int64_t B, int64_t ldb) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int n_cliques = trace[0], n_cols = trace[1];
+    int32_t* mine = assign + b * n_cols;
+    const int32_t* r = trace + 2;
+    for (int c = 0; c < n_cliques; ++c) {
+        const int64_t off = ld_i64(r);
+        const int n_ax = r[2];
+        const int32_t* ax = r + 3;
+        int64_t base = off;
+        int64_t n_new = 1;
+        for (int a = 0; a < n_ax; ++a) {
+            if (ax[4 * a + 3]) n_new *= ax[4 * a + 1];
+            else base += (int64_t)mine[ax[4 * a]] * ax[4 * a + 2];
+        }
+        // enumerate the new axes in C-order (last new axis fastest) with an odometer over their digits
+        int digit[MAX_AXES];
+        for (int a = 0; a < n_ax; ++a) digit[a] = 0;
+        T best = neg_inf<T>();
+        int64_t arg = 0, rel = 0;
+        for (int64_t k = 0; k < n_new; ++k) {
+            const T v = ws[(base + rel) * ldb + b];
+            if (v > best || (k == 0)) {
+                best = v;
+                arg = k;
+            }
+            for (int a = n_ax - 1; a >= 0; --a) {
+                if (!ax[4 * a + 3]) continue;
+                rel += ax[4 * a + 2];
+                if (++digit[a] < ax[4 * a + 1]) break;
+                rel -= (int64_t)digit[a] * ax[4 * a + 2];
+                digit[a] = 0;
+            }
+        }
+        for (int a = n_ax - 1; a >= 0; --a) {
+            if (!ax[4 * a + 3]) continue;
+            const int d = ax[4 * a + 1];
+            mine[ax[4 * a]] = (int32_t)(arg % d);
+            arg /= d;
+        }
+        r += 3 + 4 * n_ax;
+    }
+}
+
 // first index of the row maximum (numpy.argmax semantics: first occurrence; NaN propagates like numpy: a NaN wins)
 template <typename T>
 __global__ void __launch_bounds__(128) k_argmax_rows(const T* __restrict__ src, int64_t n, int64_t B, int32_t* __restrict__ out) {
@@ -764,6 +817,9 @@ struct pgx_plan {
     // table-driven fused kernel (pgx_fused.cuh)
     pgx::MicroInfo micro;
     int32_t* d_micro = nullptr;
+    // max-product traceback descriptor (pgx_plan_set_trace)
+    int32_t* d_trace = nullptr;
+    int trace_cols = 0;
     // options
     int mode = PGX_MODE_AUTO;
     int fused_warps = 0;  // 0 = auto
@@ -961,6 +1017,7 @@ void pgx_plan_destroy(pgx_plan* plan) {
     if (!plan) return;
     if (plan->d_pool) cudaFree(plan->d_pool);
     if (plan->d_micro) cudaFree(plan->d_micro);
+    if (plan->d_trace) cudaFree(plan->d_trace);
     for (GraphEntry& g : plan->graphs) cudaGraphExecDestroy(g.exec);
     for (StepSchedule& c : plan->schedules) c.release();
     if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
@@ -1454,6 +1511,65 @@ int pgx_run_batch_soft(pgx_plan* plan, const int32_t* ev_states, const void* sof
     cudaStream_t st = (cudaStream_t)stream;
     if (plan->dtype == PGX_F64) return run_typed<double>(plan, ev_states, soft, out, workspace, B, st);
     return run_typed<float>(plan, ev_states, soft, out, workspace, B, st);
+}
+
+int pgx_plan_set_trace(pgx_plan* plan, const int32_t* trace, int64_t n_words) {
+    if (!plan || !trace || n_words < 2) return fail(PGX_ERR_INVALID, "bad argument");
+    const int n_cliques = trace[0], n_cols = trace[1];
+    if (n_cliques < 1 || n_cols < 1) return fail(PGX_ERR_INVALID, "empty traceback descriptor");
+    int64_t at = 2;
+    std::vector<char> seen((size_t)n_cols, 0);
+    for (int c = 0; c < n_cliques; ++c) {
+        if (at + 3 > n_words) return fail(PGX_ERR_INVALID, "traceback descriptor truncated");
+        const int64_t off = ld_i64(trace + at);
+        const int n_ax = trace[at + 2];
+        if (n_ax < 0 || n_ax > MAX_AXES || at + 3 + 4LL * n_ax > n_words) return fail(PGX_ERR_INVALID, "traceback descriptor truncated");
+        int64_t hi = off;
+        for (int a = 0; a < n_ax; ++a) {
+            const int32_t* ax = trace + at + 3 + 4 * a;
+            if (ax[0] < 0 || ax[0] >= n_cols || ax[1] < 1 || ax[2] < 0) return fail(PGX_ERR_INVALID, "bad traceback axis");
+            if (ax[3]) {
+                if (seen[ax[0]]) return fail(PGX_ERR_INVALID, "traceback column assigned twice");
+                seen[ax[0]] = 1;
+            } else if (!seen[ax[0]]) {
+                return fail(PGX_ERR_INVALID, "traceback reads a column before it is assigned");
+            }
+            hi += (int64_t)(ax[1] - 1) * ax[2];
+        }
+        if (off < 0 || hi >= plan->ws_entries) return fail(PGX_ERR_BOUNDS, "traceback table outside workspace");
+        at += 3 + 4 * n_ax;
+    }
+    for (int i = 0; i < n_cols; ++i)
+        if (!seen[i]) return fail(PGX_ERR_INVALID, "traceback leaves a column unassigned");
+    if (plan->d_trace) cudaFree(plan->d_trace);
+    plan->d_trace = nullptr;
+    PGX_CUDA(cudaMalloc((void**)&plan->d_trace, (size_t)n_words * sizeof(int32_t)));
+    PGX_CUDA(cudaMemcpy(plan->d_trace, trace, (size_t)n_words * sizeof(int32_t), cudaMemcpyHostToDevice));
+    plan->trace_cols = n_cols;
+    return PGX_OK;
+}
+
+int pgx_run_batch_mpe(pgx_plan* plan, const int32_t* ev_states, const void* soft, int32_t* assign, void* workspace,
+                      size_t workspace_bytes, int64_t B, void* stream) {
+    if (!plan || !assign) return fail(PGX_ERR_INVALID, "null argument");
+    if (!plan->d_trace) return fail(PGX_ERR_INVALID, "plan has no traceback descriptor (pgx_plan_set_trace)");
+    if (plan->out_elems != 0) return fail(PGX_ERR_INVALID, "a max-product plan has no output segments");
+    const int saved_mode = plan->mode;
+    plan->mode = PGX_MODE_STEPWISE;  // the traceback reads the beliefs from the global workspace
+    const int rc = pgx_run_batch_soft(plan, ev_states, soft, nullptr, workspace, workspace_bytes, B, stream);
+    plan->mode = saved_mode;
+    if (rc != PGX_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ldb = pgx_batch_ld(B);
+    const size_t head = ((size_t)plan->table_entries + 31) / 32 * 32;
+    const unsigned grid = (unsigned)((B + 127) / 128);
+    if (plan->dtype == PGX_F64)
+        k_mpe_traceback<double><<<grid, 128, 0, st>>>(plan->d_trace, (const double*)workspace + head, assign, B, ldb);
+    else
+        k_mpe_traceback<float><<<grid, 128, 0, st>>>(plan->d_trace, (const float*)workspace + head, assign, B, ldb);
+    PGX_CUDA(cudaGetLastError());
+    plan->last_launches += 1;
+    return PGX_OK;
 }
 
 // Shared body of the two tracing entry points: a stepwise pass with one CUDA event per launch.

@@ -190,6 +190,48 @@ class CompiledPlan:
             )
         return out
 
+    def set_trace(self, trace: np.ndarray):
+        """Attach the traceback descriptor of a max-product plan (planner.compile_jt_mpe_plan)."""
+        trace = np.ascontiguousarray(trace, dtype=np.int32)
+        N.check(self.lib.pgx_plan_set_trace(self.handle, trace.ctypes.data_as(C.POINTER(C.c_int32)), trace.size))
+        self.trace_cols = int(trace[1])
+
+    def run_mpe(self, ev_states, soft=None):
+        """Max-product pass + traceback: int32 CUDA tensor [B, n_columns] of state indices (most probable explanation of
+        every unobserved variable, column order of the descriptor). Batches whose workspace would exceed the cap are
+        processed in row tiles."""
+        torch = _torch()
+        if not getattr(self, "trace_cols", 0):
+            raise ValueError("not a max-product plan: call set_trace first")
+        if self.n_ev:
+            if ev_states.dtype != torch.int32 or not ev_states.is_cuda or not ev_states.is_contiguous() or \
+                    ev_states.dim() != 2 or ev_states.shape[1] != self.n_ev:
+                raise ValueError(f"ev_states must be a contiguous int32 CUDA tensor [B, {self.n_ev}]")
+            B_all = int(ev_states.shape[0])
+        else:
+            B_all = int(soft.shape[0]) if soft is not None else 1
+        if self.plan.in_elems and (soft is None or soft.shape != (B_all, self.plan.in_elems) or soft.dtype != self.torch_dtype):
+            raise ValueError(f"soft must be a {self.dtype_name} CUDA tensor [B, {self.plan.in_elems}]")
+        with torch.cuda.device(self.device):
+            out = torch.empty((B_all, self.trace_cols), dtype=torch.int32, device=self.device)
+            tile = B_all
+            if B_all > 32 and self.workspace_bytes(B_all) > self.MAX_WORKSPACE_BYTES:
+                per_set = self.workspace_bytes(32) // 32
+                tile = max(32, int(self.MAX_WORKSPACE_BYTES // max(per_set, 1)) // 32 * 32)
+            tile = min(tile, self.MAX_ROWS_PER_PASS)
+            need = self.workspace_bytes(min(tile, B_all))
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            for lo in range(0, B_all, tile):
+                hi = min(B_all, lo + tile)
+                ev = ev_states[lo:hi] if self.n_ev else None
+                sf = soft[lo:hi].contiguous() if soft is not None else None
+                N.check(self.lib.pgx_run_batch_mpe(
+                    self.handle, C.c_void_p(ev.data_ptr() if ev is not None else 0), C.c_void_p(sf.data_ptr() if sf is not None else 0),
+                    C.c_void_p(out[lo:hi].data_ptr()), C.c_void_p(self._ws.data_ptr()), self._ws.numel(), hi - lo, C.c_void_p(stream)))
+        return out
+
     def profile_steps(self, ev_states):
         """Per-step device time (ms) of one stepwise pass: list of (ms, out_size, sum_size, n_operands, alg_bytes)."""
         torch = _torch()

@@ -380,7 +380,14 @@ class VariableElimination(_Inference):
             virt = {"__" + str(c.variables[0]): 0 for c in virtual_evidence}
             return sub.map_query(variables, {**evidence, **virt}, None, elimination_order, show_progress)
         if not variables:
-            order = list(self.model.nodes()) if not isinstance(self.model, JunctionTree) else sorted(self.variables, key=str)
+            if isinstance(self.model, DiscreteBayesianNetwork):
+                # every unobserved variable (nothing is pruned then): junction-tree max-product with back-pointers
+                # instead of the full joint table (BeliefPropagation.mpe_batch)
+                bp = getattr(self, "_mpe_bp", None)
+                if bp is None:
+                    bp = self._mpe_bp = BeliefPropagation(self.model, dtype=self.dtype)
+                return bp.map_query(None, evidence)
+            order = sorted(self.variables, key=str)
             variables = [v for v in order if v not in evidence]
         variables = list(variables)
         evidence = self._check_query(variables, evidence)
@@ -555,17 +562,53 @@ class BeliefPropagation(_Inference):
             virt = {"__" + str(c.variables[0]): 0 for c in virtual_evidence}
             return sub.map_query(variables, {**evidence, **virt}, None, show_progress)
         if not variables:
-            seen = []
-            for c in self._jt.cliques:
-                for v in c:
-                    if v not in seen and v not in evidence:
-                        seen.append(v)
-            variables = seen
+            # every unobserved variable: max-product with back-pointers (the joint table the reference maximises would
+            # have prod(card) entries)
+            evidence = self._check_query([], evidence, allow_empty=True)
+            ev_vars = list(evidence)
+            columns, assign = self.mpe_batch(ev_vars, self._states_of(ev_vars, [evidence]))
+            row = assign[0].cpu().numpy()
+            return {v: self.states[v][int(s)] for v, s in zip(columns, row)}
         joint = self.query(list(variables), evidence=evidence, joint=True)
         torch = require_cuda()
         t = torch.from_numpy(np.ascontiguousarray(joint.values.reshape(1, -1))).cuda()
         idx = int(VariableElimination._argmax_rows(self, t)[0].item())
         return VariableElimination._decode(self, list(variables), idx)
+
+    def mpe_plan(self, evidence_vars, soft_vars=()):
+        """(compiled max-product plan with its traceback attached, the variable of each output column)."""
+        key = ("jt-mpe", tuple(evidence_vars), tuple(soft_vars))
+        hit = self._plans.get(key)
+        if hit is None:
+            plan, trace, columns = PL.compile_jt_mpe_plan(self._jt, list(evidence_vars), soft_vars=soft_vars)
+            cp = self._compile(plan)
+            cp.set_trace(trace)
+            hit = (cp, columns)
+            self._plans[key] = hit
+        return hit
+
+    def mpe_batch(self, evidence_vars, evidence_states, virtual_evidence=None):
+        """Most probable explanation of ALL unobserved variables for B evidence sets: max-product
+        on the junction tree with back-pointers instead of the reference's argmax over the full joint table
+        (ExactInference.py:609-612, :1222-1317 — 10^15 entries on alarm). Returns (variables, int32 CUDA tensor
+        [B, len(variables)] of state indices). Among exactly tied maxima the first in clique order wins, which need not
+        be the reference's first-in-joint-order choice; the joint probability of the answer is the same."""
+        torch = require_cuda()
+        self._check_query([], {v: None for v in evidence_vars}, allow_empty=True)
+        soft_vars = tuple(_soft_items(self, virtual_evidence)) if virtual_evidence else ()
+        cp, columns = self.mpe_plan(evidence_vars, soft_vars)
+        ev_t = None
+        if cp.n_ev:
+            if isinstance(evidence_states, np.ndarray) or not hasattr(evidence_states, "is_cuda"):
+                ev = np.ascontiguousarray(np.asarray(evidence_states, dtype=np.int32)).reshape(-1, cp.n_ev)
+                for j, v in enumerate(cp.plan.ev_vars):
+                    if ev.shape[0] and (ev[:, j].min() < 0 or ev[:, j].max() >= self.cardinality[v]):
+                        raise ValueError(f"evidence state index out of range for variable {v}")
+                ev_t = torch.from_numpy(ev).to(cp.device)
+            else:
+                ev_t = evidence_states
+        soft = self._soft_rows(cp, virtual_evidence, int(ev_t.shape[0]) if ev_t is not None else None) if soft_vars else None
+        return columns, cp.run_mpe(ev_t, soft)
 
     def marginals_plan(self, evidence_vars, variables=None, soft_vars=()) -> CompiledPlan:
         """Compiled all-marginals plan for one evidence-variable signature (bench / batched callers)."""

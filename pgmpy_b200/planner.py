@@ -688,6 +688,81 @@ def compile_jt_plan(
     )
 
 
+def compile_jt_mpe_plan(jt: JTStructure, evidence_vars: Sequence[Hashable] = (), soft_vars: Sequence[Hashable] = ()):
+    """Most probable explanation over ALL unobserved variables by max-product on the junction tree with back-pointers
+    (SURVEY.md §8f rank 1). The reference's map_query maximises the full joint table (ExactInference.py:609-612,
+    :1222-1317) — 10^15 entries on alarm; this computes the same argmax in two passes:
+
+      collect (max):  m[i->p] = max over (C_i minus S_ip) of psi_i[E=e] * prod_{c in ch(i)} m[c->i]
+      upward beliefs: beta_i = psi_i[E=e] * prod_{c in ch(i)} m[c->i]      (kept in the workspace, one per clique)
+      traceback (k_mpe_traceback, root first): the variables of C_i not fixed by an ancestor take the argmax of beta_i
+                      restricted to the already fixed ones (first maximum in C-order, like numpy.argmax).
+
+    Returns (plan, trace, columns): the plan has no output segments; `trace` is the int32 descriptor the traceback
+    kernel walks — n_cliques | n_columns | per clique in pre-order: work offset lo, hi | n_axes | n_axes x (column,
+    cardinality, stride in beta_i, 1 if the axis is assigned here) — and `columns` the variable of each output column."""
+    ev = list(evidence_vars)
+    evset = set(ev)
+    card = jt.card
+    b = PlanBuilder(card, ev)
+    n = len(jt.cliques)
+    free = [tuple(v for v in c if v not in evset) for c in jt.cliques]
+    psi: List[List[Table]] = []
+    for i in range(n):
+        psi.append([b.add_const(sc, vals) for sc, vals in jt.factors[i] if not all(v in evset for v in sc)])
+    for v in soft_vars:
+        if v in evset:
+            raise ValueError(f"soft evidence on the observed variable {v}")
+        home = [i for i in range(n) if v in jt.cliques[i]]
+        i = min(home, key=lambda i: (int(np.prod([card[u] for u in free[i]], dtype=np.int64)), i))
+        psi[i] = psi[i] + [b.add_input([v])]
+    ones: Dict[Hashable, Table] = {}
+
+    def covered(ops, need):
+        have = set(v for t in ops for v in t.vars)
+        extra = []
+        for v in need:
+            if v not in have:
+                if v not in ones:
+                    ones[v] = b.add_const([v], np.ones(card[v]))
+                extra.append(ones[v])
+        return list(ops) + extra
+
+    up: Dict[int, Table] = {}
+    beta: Dict[int, Table] = {}
+    for i in reversed(jt.pre):
+        ops = covered(psi[i] + [up[c] for c in jt.children[i]], free[i])
+        beta[i] = b.contract(ops, free[i], level=2 * jt.height[i], optimize=False, split=False)
+        beta[i].last_step = 1 << 60  # read by the traceback kernel after the last step
+        p = jt.parent[i]
+        if p >= 0:
+            sp = set(jt.cliques[p])
+            s_ip = tuple(v for v in free[i] if v in sp)
+            up[i] = b.contract([beta[i]], s_ip, level=2 * jt.height[i] + 1, reduce_max=True, optimize=False, split=False)
+    plan = b.finalize({"mode": "jt-mpe", "evidence_vars": tuple(ev), "root": jt.root, "n_cliques": n,
+                       "soft_vars": tuple(soft_vars)})
+    columns: List[Hashable] = []
+    col_of: Dict[Hashable, int] = {}
+    trace = [n, 0]
+    for i in jt.pre:
+        t = beta[i]
+        strides = {}
+        acc = 1
+        for v in reversed(t.vars):
+            strides[v] = acc
+            acc *= card[v]
+        lo, hi = int(t.offset) & 0xFFFFFFFF, int(t.offset) >> 32
+        trace += [lo - (1 << 32) if lo >= (1 << 31) else lo, hi, len(t.vars)]
+        for v in t.vars:
+            new = v not in col_of
+            if new:
+                col_of[v] = len(columns)
+                columns.append(v)
+            trace += [col_of[v], card[v], strides[v], 1 if new else 0]
+    trace[1] = len(columns)
+    return plan, np.asarray(trace, dtype=np.int32), columns
+
+
 # ---------------------------------------------------------------------------------------------
 # evidence state mapping (bit-exact with pgmpy/utils/state_name.py:71-84)
 # ---------------------------------------------------------------------------------------------

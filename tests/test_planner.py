@@ -308,3 +308,80 @@ def test_soft_evidence_all_marginals_plan_and_save_load(tmp_path):
     z = Plan.load(path)
     assert z.in_elems == a.in_elems and [tuple(v) for v, _, _ in z.inputs] == [tuple(v) for v, _, _ in a.inputs]
     assert rel_err(run_plan(z.pool, z.const_blob, states, soft=soft), want) <= 1e-12
+
+
+def _joint_probability(m, assignment):
+    """P(x) of a full assignment {var: state index} as the product of the CPT entries."""
+    p = 1.0
+    for cpd in m.get_cpds():
+        p *= float(cpd.values[tuple(int(assignment[v]) for v in cpd.variables)])
+    return p
+
+
+def _max_product_value(m, ev_vars, ev_row):
+    """max over the unobserved variables of P(x, e): max-elimination with the oracle's factor algebra, in an order that
+    has nothing to do with the junction tree (independent check of the traceback's answer)."""
+    facs = []
+    ev = dict(zip(ev_vars, (int(s) for s in ev_row)))
+    for cpd in m.get_cpds():
+        f = O.Factor(list(cpd.variables), np.asarray(cpd.values, dtype=np.float64))
+        here = [(v, ev[v]) for v in f.variables if v in ev]
+        facs.append(O.reduce(f, here) if here else f)
+    for v in sorted((v for v in m.nodes() if v not in ev), key=str):
+        touch = [f for f in facs if v in f.variables]
+        rest = [f for f in facs if v not in f.variables]
+        prod = O.factor_product(*touch)
+        facs = rest + [O.maximize(prod, [v])]
+    val = 1.0
+    for f in facs:
+        val *= float(np.asarray(f.values).reshape(-1)[0])
+    return val
+
+
+def test_mpe_plan_and_traceback_vs_reference_golden():
+    """Max-product junction-tree plan + traceback (numpy restatement of k_mpe_traceback) against the reference's
+    map_query over every unobserved variable (tests/golden/ref_mpe_small.json, oracle/make_golden_mpe.py): same joint
+    probability to 1e-12, and the same assignment wherever the maximum is unique."""
+    import json
+    import os
+
+    from oracle.plan_exec import mpe_traceback
+    from pgmpy_b200.planner import compile_jt_mpe_plan
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "ref_mpe_small.json")) as f:
+        g = json.load(f)
+    for name in ("asia", "cancer", "sachs"):
+        m = px.get_example_model(name)
+        ev_vars = g[name]["ev_vars"]
+        states = np.asarray(g[name]["ev_states"], dtype=np.int32)
+        plan, trace, cols = compile_jt_mpe_plan(JTStructure.from_model(m), ev_vars)
+        assert plan.out_elems == 0 and set(cols) == set(m.nodes()) - set(ev_vars)
+        _, ws = run_plan(plan.pool, plan.const_blob, states, return_workspace=True)
+        asg = mpe_traceback(trace, ws)
+        for c in g[name]["cases"]:
+            full = dict(zip(ev_vars, states[c["case"]]))
+            full.update(dict(zip(cols, asg[c["case"]])))
+            p = _joint_probability(m, full)
+            assert abs(p - c["joint_probability"]) <= 1e-12 * c["joint_probability"]
+            names = {v: str(m.states[v][int(s)]) for v, s in zip(cols, asg[c["case"]])}
+            if names != c["map"]:  # only an exact tie may be resolved differently
+                assert p == c["joint_probability"], (name, c["case"])
+
+
+@pytest.mark.parametrize("name", ["alarm", "child"])
+def test_mpe_plan_reaches_the_max_product_value(name):
+    """Where the reference's full-joint argmax is infeasible (alarm: 1e15 entries): the traceback's assignment must
+    have joint probability equal to max_x P(x, e) computed by an independent max-elimination."""
+    from oracle.plan_exec import mpe_traceback
+    from pgmpy_b200.planner import compile_jt_mpe_plan
+
+    m = px.get_example_model(name)
+    ev_vars, states = sample_evidence(m, 6, 4, seed=5)
+    plan, trace, cols = compile_jt_mpe_plan(JTStructure.from_model(m), ev_vars)
+    _, ws = run_plan(plan.pool, plan.const_blob, states, return_workspace=True)
+    asg = mpe_traceback(trace, ws)
+    for b in range(len(states)):
+        full = dict(zip(ev_vars, states[b]))
+        full.update(dict(zip(cols, asg[b])))
+        want = _max_product_value(m, ev_vars, states[b])
+        assert abs(_joint_probability(m, full) - want) <= 1e-12 * want
