@@ -3,7 +3,7 @@
 TEST INFRASTRUCTURE; build container only:  python -m oracle.make_golden_beliefs
 alarm and hepar2: pgmpy.models.JunctionTree built from OUR min-fill cliques and clique potentials (the reference's own
 triangulation yields 2e7..2e8-entry cliques on alarm), BeliefPropagation(jt).calibrate(), then
-get_clique_beliefs() / get_sepset_beliefs() -> tests/golden/ref_<model>_beliefs.npz (variables in OUR clique order).
+get_clique_beliefs() / get_sepset_beliefs() -> tests/golden/beliefs_<model>.npz (variables in OUR clique order).
 The reference stops iterating when np.allclose accepts every sepset (ExactInference.py:807-895): its beliefs are exact
 to about 1e-8 relative, which is the tolerance of the test that reads this file.
 """
@@ -52,7 +52,7 @@ def main():
             perm = [f.variables.index(v) for v in vars_]
             arrays[f"s{k}"] = np.ascontiguousarray(np.transpose(np.asarray(f.values, dtype=np.float64), perm))
             sepsets.append({"a": list(jt.cliques[a]), "b": list(jt.cliques[b]), "vars": vars_})
-        path = os.path.join(OUT_DIR, f"ref_{name}_beliefs.npz")
+        path = os.path.join(OUT_DIR, f"beliefs_{name}.npz")
         header = {"model": name, "cliques": cliques, "sepsets": sepsets,
                   "reference": "pgmpy 1.0.0 BeliefPropagation(JunctionTree of our cliques/potentials).calibrate()"}
         np.savez_compressed(path, header=np.array(json.dumps(header)), **arrays)

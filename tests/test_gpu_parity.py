@@ -288,7 +288,7 @@ def test_calibrate_beliefs_vs_reference(torch_cuda, name):
 
     from pgmpy_b200.inference import BeliefPropagation
 
-    with np.load(os.path.join(os.path.dirname(__file__), "golden", f"ref_{name}_beliefs.npz")) as z:
+    with np.load(os.path.join(os.path.dirname(__file__), "golden", f"beliefs_{name}.npz")) as z:
         hdr = json.loads(str(z["header"]))
         gold = {k: z[k] for k in z.files if k != "header"}
     bp = BeliefPropagation(px.get_example_model(name))
