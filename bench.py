@@ -510,7 +510,7 @@ def run_b200(args):
             # GB/s figure below is the notional one of SURVEY 8(d) (every operand counted as if it moved)
             "bound": "l1-lsu+barrier" if fused else "hbm",
             "kernel": {"generic": "k_plan_fused", "tables-smem": "k_plan_fused2<smem>", "tables-global": "k_plan_fused2<global>"}.get(
-                variant, "k_contract_tile32 / k_contract_stage (sum over the launch sequence)"),
+                variant, "k_contract_tile32 / k_contract_mm (sum over the launch sequence)"),
             "achieved": achieved,
             "peak": peak,
             "unit": "GB/s",
@@ -640,6 +640,11 @@ def bench_config(name, bsz, args, world, rank, dev, barrier):
         "plan_compile_s": round(compile_s, 2),
         "workspace_GB": cp.workspace_bytes(bsz) / 1e9,
     }
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            res["dram_traffic_bytes_per_batch_ncu"] = json.load(f).get(f"{name}:stepwise:{bsz}")  # real HBM bytes, one ncu pass
+    except Exception:
+        res["dram_traffic_bytes_per_batch_ncu"] = None
     r1 = R01_PLAN_BYTES.get(name)
     if r1:
         # continuity with round 1, whose plans moved more bytes for the same posteriors: the same time against THAT count

@@ -25,7 +25,7 @@ print(f"{name} B={B}: plain {sum(r['ms'] for r in lp):.2f} ms, ncu {tot_t:.2f} m
 print("  i  kernel   ms(plain) ms(ncu)  alg GB  dramR  dramW  L2 GB  wavefrM  GB/s(alg) GB/s(dram)  desc")
 out = []
 for i, (r, k) in enumerate(zip(lp, last)):
-    kn = "stage" if "stage" in k["name"] else ("tile32" if "tile32" in k["name"] else ("step" if "k_contract_step" in k["name"] else k["name"][:20]))
+    kn = "mm" if "k_contract_mm" in k["name"] else "stage" if "stage" in k["name"] else ("tile32" if "tile32" in k["name"] else ("step" if "k_contract_step" in k["name"] else k["name"][:20]))
     out.append((r["ms"], i, kn, k, r))
 for ms, i, kn, k, r in sorted(out, key=lambda t: -t[0])[:top]:
     dr, dw = k["dram__bytes_read.sum"] / 1e9, k["dram__bytes_write.sum"] / 1e9
