@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(256, MAXK > 4 ? 1 : PGX_TILE_MINB) k_contract_
 // base, elements per entry) instead of two 64-bit ones, which brings the kernel to <= 40 registers — the step kernels
 // are latency bound (profiles/r01_diabetes_tile_kernel_ncu.md), so resident warps are what buys throughput.
 template <typename T, int MAXK>
-__global__ void __launch_bounds__(256, MAXK <= 4 ? PGX_TILE32_MINB : 3) k_contract_tile32(const int32_t* __restrict__ pool,
+__global__ void __launch_bounds__(256, MAXK <= 4 ? PGX_TILE32_MINB : (MAXK <= 6 ? 5 : 3)) k_contract_tile32(const int32_t* __restrict__ pool,
                                                                             const TileItem* __restrict__ items, int n_items,
                                                                             int ev_card_off, const T* __restrict__ ws_in,
                                                                             T* __restrict__ ws_out, uint32_t ws_off0,
@@ -1420,6 +1420,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                     if (idx32) {
                         if (g.max_k <= 2) PGX_LAUNCH_TILE32(2);
                         else if (g.max_k <= 4) PGX_LAUNCH_TILE32(4);
+                        else if (g.max_k <= 6) PGX_LAUNCH_TILE32(6);  // 48 registers, 40 warps per SM (pathfinder's hub belief: K = 5)
                         else PGX_LAUNCH_TILE32(8);
                     } else if (g.max_k <= 2) {
                         PGX_LAUNCH_TILE(2);

@@ -497,7 +497,12 @@ bool mm_pick(const int32_t* r, size_t item_bytes, bool allow_mma, int64_t ldb, M
         for (int a : az) Z *= odims[a];
         const int64_t K = sum_size;
         if (M < 3 || N < 3 || M > (1 << 20) || N > (1 << 20) || Z > (1 << 22)) continue;
-        const bool mma = allow_mma && !p_work && item_bytes == 8;
+        // tensor cores unless the 8-row DMMA fragments would pad M by more than 15 % (M = 11, 13, 19 ...: measured per
+        // launch on diabetes, those steps lose 30-40 % against the 4-row FMA blocks, while CPT steps with M = 100..221
+        // gain 15-20 %; profiles/r02_mm_kernel.md)
+        // (also allowing M <= 8 helps munin's M = 2..6, K = 80..100 steps by 0.6 ms but costs diabetes 3.6 ms on its
+        // M = 5, N = 11, K = 221 steps: not taken)
+        const bool mma = allow_mma && !p_work && item_bytes == 8 && ((M + 7) / 8 * 8) * 100 <= M * 115;
         const int row_bytes = 32 * (int)item_bytes;
         // tile search: blocks of 4 x 8 (FMA) or 8 x 4 (DMMA) outputs per warp, at most 16 warps
         double bc = 1e300;

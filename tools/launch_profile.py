@@ -22,6 +22,8 @@ cp = bp.marginals_plan(ev_vars)
 cp.set_mode("stepwise")
 if "nostage" in sys.argv[4:]:
     cp.set_stage(False)
+if "nomma" in sys.argv[4:]:
+    cp.set_mma(False)
 print("plan:", cp.plan.meta.get("distribute"), "factorized" if cp.plan.meta.get("factorized") else "dense", cp.plan.n_steps, "steps")
 ev = torch.from_numpy(states).cuda()
 if ncu:
@@ -53,4 +55,4 @@ for r in sorted(rows, key=lambda r: -r["ms"])[:top]:
     print(f"  {r['i']:4d} {r['ms']:8.3f} {len(r['steps']):5d} {r['alg_bytes']/1e9:8.3f} {r['alg_bytes']/max(r['ms'],1e-6)/1e6:7.0f}  {r['desc']}")
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump([{k: r[k] for k in ("i", "ms", "alg_bytes", "desc")} | {"n_steps": len(r["steps"])} for r in rows],
-          open(f"gpurun_out/launch_profile_{name}_{B}{'_nostage' if 'nostage' in sys.argv[4:] else ''}.json", "w"))
+          open(f"gpurun_out/launch_profile_{name}_{B}{'_nostage' if 'nostage' in sys.argv[4:] else ''}{'_nomma' if 'nomma' in sys.argv[4:] else ''}.json", "w"))
