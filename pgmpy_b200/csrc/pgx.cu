@@ -96,9 +96,11 @@ struct TileItem {
 // s_otab[t][k] (entry offset of operand k at summed index 0) and the summed range into s_stab[q][k]. Lanes work on
 // different entries, so no lane repeats another's mixed-radix arithmetic (ncu on munin: the per-thread decomposition
 // cost ~150 issue slots per (entry, warp) when every lane decoded the same entry).
+// `work_unit` != 0: offsets of work-table operands are stored already multiplied by it (elements per table entry = ldb),
+// so the streaming loop adds them to a row base without a multiply (32-bit-addressed kernel only).
 template <int MAXK>
 __device__ __forceinline__ void tile_decode(const int32_t* __restrict__ s_rec, int32_t* __restrict__ s_otab,
-                                            int32_t* __restrict__ s_stab, uint32_t tile0, int TO) {
+                                            int32_t* __restrict__ s_stab, uint32_t tile0, int TO, uint32_t work_unit = 0) {
     const int A = s_rec[0], S = s_rec[1], K = s_rec[2];
     const int opw = OP_FIXED + A + S;
     const int32_t* odims = s_rec + STEP_FIXED;
@@ -124,7 +126,7 @@ __device__ __forceinline__ void tile_decode(const int32_t* __restrict__ s_rec, i
         }
 #pragma unroll
         for (int k = 0; k < MAXK; ++k)
-            if (k < K) s_otab[t * K + k] = off[k];
+            if (k < K) s_otab[t * K + k] = (work_unit && (ops[k * opw] & 0xFF) == 1) ? (int32_t)((uint32_t)off[k] * work_unit) : off[k];
     }
     for (int qi = threadIdx.x; qi < sum_size; qi += blockDim.x) {
         uint32_t rem = (uint32_t)qi;
@@ -142,7 +144,7 @@ __device__ __forceinline__ void tile_decode(const int32_t* __restrict__ s_rec, i
         }
 #pragma unroll
         for (int k = 0; k < MAXK; ++k)
-            if (k < K) s_stab[qi * K + k] = off[k];
+            if (k < K) s_stab[qi * K + k] = (work_unit && (ops[k * opw] & 0xFF) == 1) ? (int32_t)((uint32_t)off[k] * work_unit) : off[k];
     }
 }
 
@@ -312,11 +314,87 @@ __global__ void __launch_bounds__(256, MAXK > 4 ? 1 : PGX_TILE_MINB) k_contract_
     }
 }
 
+// Phase 2 of k_contract_tile32 for one tile of evidence sets, specialised on the number of multiplicands NM: the
+// offset tables already hold element offsets (tile_decode with work_unit = ldb), so one operand element costs an
+// offset read, an add, the load and the multiply. (The first version ran ONE loop for every step shape: operand count
+// as a run-time predicate on a MAXK-wide body, sum and max both computed and selected, one IMAD per load — ncu on
+// munin: 38 issued instructions per (entry, summed index) of a two-operand step, 68 % issue-active on a kernel that
+// should only wait for HBM; profiles/r02_tile32_munin_ncu_raw.txt.)
+//   pm[k]  : element index of operand k's row for this lane at (entry offset 0, summed index 0)
+//   d0, d1 : the same for up to two divisors (n_div of them), whose offsets are columns NM, NM + 1 of the entry table
+template <typename T, int NM, bool MAX>
+__device__ __forceinline__ void tile32_rows(const T* __restrict__ ws_in, T* __restrict__ ws_out,
+                                            const int32_t* __restrict__ s_otab, const int32_t* __restrict__ s_stab, int K,
+                                            int sum_size, const uint32_t (&pm)[NM], int n_div, uint32_t d0, uint32_t d1,
+                                            uint32_t outb, uint32_t ldb, uint32_t tile0, uint32_t out_size, int TO, int og0,
+                                            int og_step) {
+    if (sum_size == 1 && n_div == 0) {
+        // pure product: two entries in flight per thread (the step never reads what it writes, so the loads of the second
+        // entry may be issued before the store of the first)
+        for (int og = og0; og < TO; og += 2 * og_step) {
+            const uint32_t o0 = tile0 + og, o1 = o0 + og_step;
+            if (o0 >= out_size) break;
+            const bool two = (og + og_step < TO) && (o1 < out_size);
+            const int32_t* ot0 = s_otab + og * K;
+            const int32_t* ot1 = ot0 + (two ? og_step * K : 0);
+            T v0[NM], v1[NM];
+#pragma unroll
+            for (int k = 0; k < NM; ++k) {
+                v0[k] = ws_in[pm[k] + (uint32_t)ot0[k]];
+                v1[k] = ws_in[pm[k] + (uint32_t)ot1[k]];
+            }
+            T p0 = v0[0], p1 = v1[0];
+#pragma unroll
+            for (int k = 1; k < NM; ++k) {
+                p0 *= v0[k];
+                p1 *= v1[k];
+            }
+            ws_out[outb + o0 * ldb] = p0;
+            if (two) ws_out[outb + o1 * ldb] = p1;
+        }
+        return;
+    }
+    for (int og = og0; og < TO; og += og_step) {
+        const uint32_t o = tile0 + og;
+        if (o >= out_size) break;
+        const int32_t* ot = s_otab + og * K;
+        uint32_t p[NM];
+#pragma unroll
+        for (int k = 0; k < NM; ++k) p[k] = pm[k] + (uint32_t)ot[k];
+        T acc;
+        if (sum_size == 1) {
+            acc = ws_in[p[0]];
+#pragma unroll
+            for (int k = 1; k < NM; ++k) acc *= ws_in[p[k]];
+        } else {
+            acc = MAX ? neg_inf<T>() : (T)0;
+            const int32_t* st = s_stab;
+#pragma unroll 4
+            for (int q = 0; q < sum_size; ++q, st += K) {
+                T prod = ws_in[p[0] + (uint32_t)st[0]];
+#pragma unroll
+                for (int k = 1; k < NM; ++k) prod *= ws_in[p[k] + (uint32_t)st[k]];
+                if (MAX)
+                    acc = prod > acc ? prod : acc;
+                else
+                    acc += prod;
+            }
+        }
+        if (n_div > 0) {
+            T den = ws_in[d0 + (uint32_t)ot[NM]];
+            if (n_div > 1) den *= ws_in[d1 + (uint32_t)ot[NM + 1]];
+            const T r = acc / den;
+            acc = (r != r) ? (T)0 : r;  // 0/0 -> 0 ; x/0 stays inf (DiscreteFactor.py:859-863)
+        }
+        ws_out[outb + o * ldb] = acc;
+    }
+}
+
 // K2, tile-cooperative form with 32-bit addressing (the default). Same two phases as k_contract_tile, but every
 // operand lives in ONE address space: pgx_run_batch copies the batch-invariant tables to the head of the workspace,
-// so an operand element is `wsb[u32 index]` whatever its kind. Per operand the thread keeps two 32-bit values (row
-// base, elements per entry) instead of two 64-bit ones, which brings the kernel to <= 40 registers — the step kernels
-// are latency bound (profiles/r01_diabetes_tile_kernel_ncu.md), so resident warps are what buys throughput.
+// so an operand element is `wsb[u32 index]` whatever its kind. Per operand the thread keeps one 32-bit row base, which
+// brings the kernel to 32 registers — these steps wait for HBM, so resident warps are what buys throughput. The host
+// sends a step here only if it has at most two divisors (else the generic kernel takes it).
 template <typename T, int MAXK>
 __global__ void __launch_bounds__(256, MAXK <= 4 ? PGX_TILE32_MINB : (MAXK <= 6 ? 5 : 3)) k_contract_tile32(const int32_t* __restrict__ pool,
                                                                             const TileItem* __restrict__ items, int n_items,
@@ -336,20 +414,19 @@ __global__ void __launch_bounds__(256, MAXK <= 4 ? PGX_TILE32_MINB : (MAXK <= 6 
     __syncthreads();
     const int A = s_rec[0], S = s_rec[1], K = s_rec[2], flags = s_rec[3];
     const int opw = OP_FIXED + A + S;
-    const int32_t* odims = s_rec + STEP_FIXED;
-    const int32_t* sdims = odims + A;
-    const int32_t* ops = sdims + S;
+    const int32_t* ops = s_rec + STEP_FIXED + A + S;
     const uint32_t out_size = (uint32_t)s_rec[4];
     const int sum_size = s_rec[6];
     int32_t* s_otab = s_mem + ((rec_len + 3) & ~3);
     int32_t* s_stab = s_otab + TO * K;
     const uint32_t tile0 = (uint32_t)tile_x * (uint32_t)TO;
-    tile_decode<MAXK>(s_rec, s_otab, s_stab, tile0, TO);
+    tile_decode<MAXK>(s_rec, s_otab, s_stab, tile0, TO, ldb);
     __syncthreads();
 
     int n_mul = K;
     if (flags & FLAG_DIV)
         while (n_mul > 0 && (ops[(n_mul - 1) * opw] & 0x100)) --n_mul;
+    const int n_div = K - n_mul;
     const bool use_max = (flags & FLAG_MAX) != 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const int bt = 1 << bt_log2;
@@ -358,14 +435,15 @@ __global__ void __launch_bounds__(256, MAXK <= 4 ? PGX_TILE32_MINB : (MAXK <= 6 
     const uint32_t out_base = ws_off0 + (uint32_t)s_rec[8] * ldb;  // out work offset fits 32 bits here (host checked)
     const int32_t* ev_card = pool + ev_card_off;
     const int og_step = n_warps * o_per_warp;
+    const int og0 = warp * o_per_warp + o_sub;
     for (int tb = 0; tb < btb; ++tb) {
         const int64_t b = ((int64_t)b_block * btb + tb) * bt + (lane & (bt - 1));
         if (b >= B) continue;  // no barriers below
-        uint32_t rowb[MAXK], unit[MAXK];
+        uint32_t rowb[MAXK];
+        uint32_t d0 = 0, d1 = 0;
 #pragma unroll
         for (int k = 0; k < MAXK; ++k) {
             rowb[k] = 0;
-            unit[k] = 0;
             if (k < K) {
                 const int32_t* op = ops + k * opw;
                 uint32_t e = (uint32_t)op[1];
@@ -380,77 +458,37 @@ __global__ void __launch_bounds__(256, MAXK <= 4 ? PGX_TILE32_MINB : (MAXK <= 6 
                         e += (uint32_t)(st * pairs[2 * j + 1]);
                     }
                 }
-                if ((op[0] & 0xFF) == 1) {
-                    unit[k] = ldb;
-                    rowb[k] = ws_off0 + e * ldb + (uint32_t)b;
-                } else {
-                    unit[k] = 1;
-                    rowb[k] = e;
-                }
+                rowb[k] = (op[0] & 0xFF) == 1 ? ws_off0 + e * ldb + (uint32_t)b : e;
+                if (k == n_mul) d0 = rowb[k];
+                if (k == n_mul + 1) d1 = rowb[k];
             }
         }
         const uint32_t outb = out_base + (uint32_t)b;
-        if (S == 0 && !(flags & FLAG_DIV)) {
-            for (int og = warp * o_per_warp + o_sub; og < TO; og += 2 * og_step) {
-                const uint32_t o0 = tile0 + og, o1 = o0 + og_step;
-                if (o0 >= out_size) break;
-                const bool two = (og + og_step < TO) && (o1 < out_size);
-                const int32_t* ot0 = s_otab + og * K;
-                const int32_t* ot1 = ot0 + (two ? og_step * K : 0);
-                T p0 = (T)1, p1 = (T)1;
-#pragma unroll
-                for (int k = 0; k < MAXK; ++k) {
-                    if (k < K) {
-                        const T v0 = ws_in[rowb[k] + (uint32_t)ot0[k] * unit[k]];
-                        const T v1 = ws_in[rowb[k] + (uint32_t)ot1[k] * unit[k]];
-                        p0 *= v0;
-                        p1 *= v1;
-                    }
-                }
-                ws_out[outb + o0 * ldb] = p0;
-                if (two) ws_out[outb + o1 * ldb] = p1;
-            }
-            continue;
+#define PGX_T32_CASE(NM)                                                                                                  \
+    case NM: {                                                                                                            \
+        if (NM <= MAXK) {                                                                                                 \
+            uint32_t pm[NM];                                                                                              \
+            _Pragma("unroll") for (int k = 0; k < NM; ++k) pm[k] = rowb[k < MAXK ? k : 0];                                \
+            if (use_max)                                                                                                  \
+                tile32_rows<T, NM, true>(ws_in, ws_out, s_otab, s_stab, K, sum_size, pm, n_div, d0, d1, outb, ldb, tile0, \
+                                         out_size, TO, og0, og_step);                                                     \
+            else                                                                                                          \
+                tile32_rows<T, NM, false>(ws_in, ws_out, s_otab, s_stab, K, sum_size, pm, n_div, d0, d1, outb, ldb, tile0, \
+                                          out_size, TO, og0, og_step);                                                    \
+        }                                                                                                                 \
+    } break;
+        switch (n_mul) {
+            PGX_T32_CASE(1)
+            PGX_T32_CASE(2)
+            PGX_T32_CASE(3)
+            PGX_T32_CASE(4)
+            PGX_T32_CASE(5)
+            PGX_T32_CASE(6)
+            PGX_T32_CASE(7)
+            PGX_T32_CASE(8)
+            default: break;
         }
-        for (int og = warp * o_per_warp + o_sub; og < TO; og += og_step) {
-            const uint32_t o = tile0 + og;
-            if (o >= out_size) break;
-            const int32_t* ot = s_otab + og * K;
-            uint32_t p[MAXK];
-#pragma unroll
-            for (int k = 0; k < MAXK; ++k) p[k] = (k < K) ? rowb[k] + (uint32_t)ot[k] * unit[k] : 0;
-            T acc;
-            if (S == 0) {
-                T prod = (T)1;
-#pragma unroll
-                for (int k = 0; k < MAXK; ++k)
-                    if (k < n_mul) prod *= ws_in[p[k]];
-                acc = prod;
-            } else {
-                acc = use_max ? neg_inf<T>() : (T)0;
-                const int32_t* st = s_stab;
-#pragma unroll 4
-                for (int q = 0; q < sum_size; ++q, st += K) {
-                    T prod = (T)1;
-#pragma unroll
-                    for (int k = 0; k < MAXK; ++k)
-                        if (k < n_mul) prod *= ws_in[p[k] + (uint32_t)st[k] * unit[k]];
-                    if (use_max)
-                        acc = prod > acc ? prod : acc;
-                    else
-                        acc += prod;
-                }
-            }
-            if (flags & FLAG_DIV) {
-                T den = (T)1;
-#pragma unroll
-                for (int k = 0; k < MAXK; ++k)
-                    if (k >= n_mul && k < K) den *= ws_in[p[k]];
-                const T r = acc / den;
-                acc = (r != r) ? (T)0 : r;
-            }
-            ws_out[outb + o * ldb] = acc;
-        }
+#undef PGX_T32_CASE
     }
 }
 
@@ -1271,7 +1309,16 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
             for (size_t si = 0; si < pl->steps.size(); ++si) {
                 const StepInfo& s = pl->steps[si];
                 const int64_t stab_words = s.sum_size * s.n_ops;
-                const bool tile_ok = s.n_ops <= 8 && stab_words <= 8192 && pl->step_kernel != 1;  // 0 tile32, 2 tile64
+                int n_divisors = 0;
+                {
+                    const int32_t* r0 = pl->pool.data() + s.rec_off;
+                    const int opw0 = OP_FIXED + r0[0] + r0[1];
+                    for (int k = 0; k < s.n_ops; ++k)
+                        if (r0[STEP_FIXED + r0[0] + r0[1] + k * opw0] & 0x100) ++n_divisors;
+                }
+                // (the 32-bit tile kernel keeps at most two divisor rows in registers; a step of divisors only is generic)
+                const bool tile_ok = s.n_ops <= 8 && stab_words <= 8192 && pl->step_kernel != 1 &&  // 0 tile32, 2 tile64
+                                     n_divisors <= 2 && n_divisors < s.n_ops;
                 const int32_t* srec = pl->pool.data() + s.rec_off;
                 if (s.level != cur_level || !pl->batch_levels) flush_level();
                 cur_level = s.level;
