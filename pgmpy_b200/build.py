@@ -42,6 +42,7 @@ def build_native(force=False, verbose=False):
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O3"]
     if verbose:
         flags += ["-Xptxas", "-v"]
+    flags += [f"-D{d}" for d in os.environ.get("PGX_DEFINES", "").split() if d]  # tuning builds only
     procs = []
     for src in SOURCES:
         obj = os.path.join(OBJ_DIR, os.path.basename(src) + ".o")

@@ -1281,9 +1281,10 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                     // proportion to their model cost, a run never shorter than ~20k model cycles (pipeline prologue).
                     double total = 0;
                     for (size_t i = 0; i < pending_mm.size(); ++i) total += pending_mm_cost[i] * (double)b_tiles;
-                    int waves = (int)(total / (148.0 * 100000.0));
+                    const double slots = 148.0 * MM_CTAS_PER_SM;  // CTAs resident at once
+                    int waves = (int)(total / (slots * 100000.0));
                     waves = waves < 1 ? 1 : (waves > 6 ? 6 : waves);
-                    const double target = std::max(20000.0, total / (148.0 * waves));
+                    const double target = std::max(20000.0, total / (slots * waves));
                     int nb = 0;
                     for (size_t i = 0; i < pending_mm.size(); ++i) {
                         MMItem& mi = pending_mm[i];

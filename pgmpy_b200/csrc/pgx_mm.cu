@@ -17,7 +17,7 @@
 //     dedicated producer warp would leave 96 registers per thread: the 17th warp lands on one scheduler, and
 //     setmaxnreg cannot fix that because ptxas does not confine the producer code to the reduced count); row
 //     addresses come from offset tables the host tabulated per step;
-//   * the 16 warps each own a 4 x 8 register block of the tile: per summed index 4 + 8 shared-memory row reads
+//   * the 8 warps of a CTA (two CTAs per SM) each own a 4 x 8 register block of the tile: per summed index 4 + 8 shared-memory row reads
 //     feed 32 fused multiply-adds (the streaming kernel: 64 loads), full/empty mbarriers per stage, no __syncthreads
 //     in the pipeline;
 //   * a batch-invariant P (a CPT: "[M x K] . [K x (N . B)]", the evidence batch folded into the matrix N dimension) is
@@ -237,7 +237,7 @@ __device__ __forceinline__ void fma_chunk(const T* __restrict__ sp, const T* __r
 }
 
 template <typename T>
-__global__ void __launch_bounds__(MM_THREADS, 1) k_contract_mm(const MMItem* __restrict__ items, int n_items,
+__global__ void __launch_bounds__(MM_THREADS, MM_CTAS_PER_SM) k_contract_mm(const MMItem* __restrict__ items, int n_items,
                                                                 const int32_t* __restrict__ tabs,
                                                                 const T* __restrict__ ws_in, T* __restrict__ ws_out,
                                                                 uint32_t ws_off0, int64_t B, uint32_t ldb, int b_tiles) {
@@ -504,7 +504,7 @@ bool mm_pick(const int32_t* r, size_t item_bytes, bool allow_mma, int64_t ldb, M
         // M = 5, N = 11, K = 221 steps: not taken)
         const bool mma = allow_mma && !p_work && item_bytes == 8 && ((M + 7) / 8 * 8) * 100 <= M * 115;
         const int row_bytes = 32 * (int)item_bytes;
-        // tile search: blocks of 4 x 8 (FMA) or 8 x 4 (DMMA) outputs per warp, at most 16 warps
+        // tile search: blocks of 4 x 8 (FMA) or 8 x 4 (DMMA) outputs per warp, one block per warp
         double bc = 1e300;
         int b_lgTX = 0, b_lgTY = 0, b_TZ = 0, b_lgKC = 0, b_stages = 0;
         for (int lgTX = mma ? 3 : 2; lgTX <= 6; ++lgTX) {

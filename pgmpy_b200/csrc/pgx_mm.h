@@ -8,11 +8,17 @@
 
 namespace pgx {
 
-constexpr int MM_WARPS = 16;                            // warps per CTA: each copies its share of the stage rows and owns one
+// Warps per CTA. 8 = two CTAs per SM, measured best overall (diabetes / munin, ms): 16 warps x 1 CTA 53.9 / 34.1,
+// 8 x 2 53.2 / 33.0, 4 x 4 54.6 / 32.6 — smaller CTAs overlap each other's chunk boundaries, larger tiles re-read less.
+#ifndef PGX_MM_WARPS
+#define PGX_MM_WARPS 8
+#endif
+constexpr int MM_WARPS = PGX_MM_WARPS;                  // warps per CTA: each copies its share of the stage rows and owns one
 constexpr int MM_CONSUMERS = MM_WARPS;                  // 4 x 8 register block of the tile (128 registers per thread)
 constexpr int MM_THREADS = 32 * MM_WARPS;
+constexpr int MM_CTAS_PER_SM = 16 / MM_WARPS;           // 16 warps x 128 registers fill the register file either way
 constexpr int MM_MAX_STAGES = 8;
-constexpr size_t MM_SMEM_BUDGET = 208 * 1024;           // bytes of shared memory for the stage ring
+constexpr size_t MM_SMEM_BUDGET = (MM_CTAS_PER_SM == 1 ? 208 : (MM_CTAS_PER_SM == 2 ? 110 : 54)) * 1024;  // stage ring, per CTA
 
 // One step of a k_contract_mm launch. A two-operand sum-product step
 //     out[o, b] = sum_s P[ip(o, s), b] * Q[iq(o, s), b]
