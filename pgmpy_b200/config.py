@@ -46,6 +46,9 @@ class Config:
         self.DEVICE: Optional[str] = None  # None = the current CUDA device
         self.SHOW_PROGRESS = True
         self._dtype_set = False
+        # range-check evidence state indices that are handed over as CUDA tensors (one device reduction + host sync per
+        # call); host arrays are always checked. Off by default: the kernels clamp into range for memory safety.
+        self.validate_device_evidence = False
 
     def set_backend(self, backend: str = "b200", device: Optional[str] = None, dtype=None):
         if backend != "b200":

@@ -863,6 +863,7 @@ struct pgx_plan {
     int fused_warps = 0;  // 0 = auto
     int use_graph = 1;    // stepwise: replay the step sequence as a CUDA graph
     std::vector<GraphEntry> graphs;
+    GraphEntry graph_candidate{};  // argument tuple of the last graph-cache miss (exec unused)
     std::vector<StepSchedule> schedules;
     cudaStream_t cap_stream = nullptr;
     int last_graph = 0;
@@ -1503,7 +1504,15 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                 if (g.B == B && g.ev == (const void*)ev && g.soft == soft_v && g.out == out_v && g.ws == ws_v && g.step_kernel == pl->step_kernel &&
                     g.dtype_size == (int)sizeof(T))
                     hit = &g;
-            if (!hit) {
+            // capture + instantiate cost as much as dozens of direct passes (munin: thousands of nodes), so a tuple is
+            // captured only when it shows up a second time in a row of misses: callers that hand over fresh buffers on
+            // every call (out[lo:hi] slices, new evidence tensors) then never pay for a graph they will not replay
+            const GraphEntry key{B, (const void*)ev, soft_v, out_v, ws_v, pl->step_kernel, (int)sizeof(T), 0, nullptr};
+            const GraphEntry& c = pl->graph_candidate;
+            const bool seen_before = c.B == key.B && c.ev == key.ev && c.soft == key.soft && c.out == key.out && c.ws == key.ws &&
+                                     c.step_kernel == key.step_kernel && c.dtype_size == key.dtype_size;
+            if (!hit && !seen_before) pl->graph_candidate = key;
+            if (!hit && seen_before) {
                 if (!pl->cap_stream) PGX_CUDA(cudaStreamCreateWithFlags(&pl->cap_stream, cudaStreamNonBlocking));
                 cudaGraph_t graph = nullptr;
                 PGX_CUDA(cudaStreamBeginCapture(pl->cap_stream, cudaStreamCaptureModeThreadLocal));
@@ -1515,6 +1524,8 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                     cudaGraphDestroy(graph);
                     if (ce == cudaSuccess) {
                         if (pl->graphs.size() >= 8) {
+                            // the evicted executable may still be running on another stream of the caller
+                            cudaDeviceSynchronize();
                             cudaGraphExecDestroy(pl->graphs.front().exec);
                             pl->graphs.erase(pl->graphs.begin());
                         }

@@ -162,7 +162,19 @@ class _Inference:
                     raise ValueError(f"evidence state index out of range for variable {v}")
             ev_t = torch.from_numpy(ev).to(cp.device)
         else:
+            # evidence already on the GPU: it must live on the plan's device; its values are range-checked on the device
+            # only when config.validate_device_evidence is on (a min/max reduction + one host sync per call) — the kernels
+            # clamp out-of-range states into [0, card) for memory safety, so without the check a bad index yields a
+            # plausible posterior for the clamped state instead of the ValueError the host-array path raises
             ev_t = ev_states
+            if ev_t.device != cp.device:
+                raise ValueError(f"evidence_states is on {ev_t.device}, the plan on {cp.device}")
+            if config.validate_device_evidence and ev_t.numel():
+                lo = ev_t.amin(dim=0).cpu().numpy()
+                hi = ev_t.amax(dim=0).cpu().numpy()
+                for j, v in enumerate(cp.plan.ev_vars):
+                    if lo[j] < 0 or hi[j] >= self.cardinality[v]:
+                        raise ValueError(f"evidence state index out of range for variable {v}")
         return cp.run(ev_t, soft=soft)
 
     @staticmethod
@@ -262,7 +274,8 @@ class VariableElimination(_Inference):
     def query_batch(self, variables, evidence_vars, evidence_states, joint=True, elimination_order=None,
                     virtual_evidence=None):
         """One signature, B evidence sets. evidence_states: int32 [B, k] state INDICES (host array or CUDA
-        tensor) in `evidence_vars` order. `virtual_evidence`: [(variable, likelihoods [B, card]), ...] — soft evidence
+        tensor) in `evidence_vars` order; a host array is range-checked (ValueError), a CUDA tensor is clamped into
+        range by the kernels unless `config.validate_device_evidence` is set. `virtual_evidence`: [(variable, likelihoods [B, card]), ...] — soft evidence
         that differs per evidence set (semantics of inference/base.py:256-299 per row).
         Returns a CUDA tensor [B, out_elems]: the joint over `variables` (row-major in the given order) or the
         concatenated per-variable marginals when joint=False."""
@@ -405,6 +418,19 @@ class VariableElimination(_Inference):
         torch = require_cuda()
         variables = list(variables)
         self._check_query(variables, {v: None for v in evidence_vars})
+        joint_size = 1
+        for v in variables:
+            joint_size *= self.cardinality[v]
+        if (isinstance(self.model, DiscreteBayesianNetwork) and joint_size > (1 << 22)
+                and set(variables) | set(evidence_vars) == set(self.variables)):
+            # every unobserved variable is asked for (what predict() does for rows with many missing columns) and the
+            # joint table would not fit: max-product with back-pointers gives the same argmax (ties aside)
+            bp = getattr(self, "_mpe_bp", None)
+            if bp is None:
+                bp = self._mpe_bp = BeliefPropagation(self.model, dtype=self.dtype)
+            cols, assign = bp.mpe_batch(list(evidence_vars), evidence_states)
+            order = torch.as_tensor([cols.index(v) for v in variables], device=assign.device)
+            return assign.index_select(1, order).contiguous()
         joint = self._joint_for_map(variables, list(evidence_vars), evidence_states)
         flat = self._argmax_rows(joint).to(torch.int64)
         cols = []

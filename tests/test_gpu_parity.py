@@ -735,6 +735,19 @@ def test_engine_argument_errors(torch_cuda):
     # out-of-range states handed over on the device are clamped in-kernel (memory safety), never read out of bounds
     ev_bad = torch.from_numpy(bad).cuda()
     assert torch.isfinite(cp.run(ev_bad)[1:]).all()
+    # ... and rejected like host arrays when config.validate_device_evidence is on
+    from pgmpy_b200 import config
+    from pgmpy_b200.inference import BeliefPropagation
+
+    bp = BeliefPropagation(m)
+    assert torch.isfinite(bp.marginals_batch(ev_vars, ev_bad)[1:]).all()
+    config.validate_device_evidence = True
+    try:
+        with pytest.raises(ValueError):
+            bp.marginals_batch(ev_vars, ev_bad)
+        assert torch.isfinite(bp.marginals_batch(ev_vars, ev)).all()
+    finally:
+        config.validate_device_evidence = False
     with pytest.raises(PgxError):
         cp.set_mode("fused", 99)
 
@@ -873,3 +886,16 @@ def test_batched_mpe_with_traceback(torch_cuda):
         like[:, int(want[0, 0])] = 0.0
         _, moved = bp.mpe_batch(ev_vars, states, virtual_evidence=[(v, like)])
         assert int(moved[0, 0]) != int(want[0, 0])
+    # predict() on a frame whose rows leave most of alarm unobserved: the joint over the 31 missing variables has 1e15
+    # entries; the batched MAP goes through the traceback and must agree with mpe_batch
+    import pandas as pd
+
+    m = px.get_example_model("alarm")
+    ev_vars, states = sample_evidence(m, 5, 6, seed=2)
+    frame = pd.DataFrame({v: [m.states[v][int(s)] for s in states[:, j]] for j, v in enumerate(ev_vars)})
+    pred = m.predict(frame)
+    cols, asg = BeliefPropagation(m).mpe_batch(ev_vars, states)
+    asg = asg.cpu().numpy()
+    for r in range(5):
+        for j, v in enumerate(cols):
+            assert pred.iloc[r][v] == m.states[v][int(asg[r, j])]
