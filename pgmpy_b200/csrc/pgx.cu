@@ -1282,14 +1282,19 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                 cur_stage = LaunchGroup();
                 if (cur_mm.n_items > 0) {
                     // split every step's tiles into CTA-sized runs. One CTA per SM is resident (the stage ring takes the
-                    // shared memory), so the launch gets a whole number of waves: `waves` x 148 CTAs dealt to the steps in
-                    // proportion to their model cost, a run never shorter than ~20k model cycles (pipeline prologue).
+                    // shared memory), so the launch gets a whole number of waves: `waves` x resident CTAs dealt to the steps in
+                    // proportion to their model cost, a run never shorter than ~8k model cycles (pipeline prologue).
                     double total = 0;
                     for (size_t i = 0; i < pending_mm.size(); ++i) total += pending_mm_cost[i] * (double)b_tiles;
                     const double slots = 148.0 * MM_CTAS_PER_SM;  // CTAs resident at once
-                    int waves = (int)(total / (slots * 100000.0));
-                    waves = waves < 1 ? 1 : (waves > 6 ? 6 : waves);
-                    const double target = std::max(20000.0, total / (slots * waves));
+                    // measured (diabetes / munin, ms): one wave of long runs 53.2 / 32.9; runs of ~12k model cycles (several
+                    // waves, dynamically scheduled: the cost model's errors even out) 50.0 / 31.9; shorter runs 50.5-50.8
+                    double wave_cycles = 12000.0, min_cycles = 8000.0;
+                    if (const char* e = std::getenv("PGX_MM_WAVE_CYCLES")) wave_cycles = std::atof(e);  // tuning knobs
+                    if (const char* e = std::getenv("PGX_MM_MIN_CYCLES")) min_cycles = std::atof(e);
+                    int waves = (int)(total / (slots * wave_cycles));
+                    waves = waves < 1 ? 1 : (waves > 48 ? 48 : waves);
+                    const double target = std::max(min_cycles, total / (slots * waves));
                     int nb = 0;
                     for (size_t i = 0; i < pending_mm.size(); ++i) {
                         MMItem& mi = pending_mm[i];

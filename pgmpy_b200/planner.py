@@ -732,6 +732,10 @@ def compile_jt_mpe_plan(jt: JTStructure, evidence_vars: Sequence[Hashable] = (),
     beta: Dict[int, Table] = {}
     for i in reversed(jt.pre):
         ops = covered(psi[i] + [up[c] for c in jt.children[i]], free[i])
+        if not ops:
+            # every variable of the clique is observed and it has no children: a constant (its factors only scale the
+            # joint by a number that does not depend on the unobserved variables, irrelevant for the argmax)
+            ops = [b.add_const([], np.ones(()), key=("one",))]
         beta[i] = b.contract(ops, free[i], level=2 * jt.height[i], optimize=False, split=False)
         beta[i].last_step = 1 << 60  # read by the traceback kernel after the last step
         p = jt.parent[i]
