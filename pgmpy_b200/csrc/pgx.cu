@@ -1376,7 +1376,9 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                     ns.groups.push_back(g);
                     continue;
                 }
-                int btb = (int)(tile_b_tiles < 4 ? tile_b_tiles : 4);
+                static const int knob_btb = std::getenv("PGX_TILE_BTB") ? std::atoi(std::getenv("PGX_TILE_BTB")) : 4;        // tuning knobs
+                static const int knob_to = std::getenv("PGX_TILE_TO_CAP") ? std::atoi(std::getenv("PGX_TILE_TO_CAP")) : 1024;  // measured 256..1024 x btb 2..8: within 2 %, 1024 x 4 best on munin/pathfinder
+                int btb = (int)(tile_b_tiles < knob_btb ? tile_b_tiles : knob_btb);
                 int64_t b_blocks = (tile_b_tiles + btb - 1) / btb;
                 int64_t TO = (s.out_size * b_blocks) / (148 * 4);  // aim at >= 4 CTAs per SM when there is work
                 if (TO < 8 * o_per_warp) {
@@ -1385,8 +1387,8 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                     b_blocks = tile_b_tiles;
                     TO = 8 * o_per_warp;
                 }
-                if (TO > 512) TO = 512;
-                if (TO * s.n_ops > 2048) TO = 2048 / s.n_ops;
+                if (TO > knob_to) TO = knob_to;
+                if (TO * s.n_ops > 4 * knob_to) TO = 4 * knob_to / s.n_ops;
                 TO = (TO + o_per_warp - 1) / o_per_warp * o_per_warp;
                 if (TO > s.out_size) TO = (s.out_size + o_per_warp - 1) / o_per_warp * o_per_warp;
                 LaunchGroup& cg = cur;

@@ -403,6 +403,15 @@ def test_standalone_gather_and_normalize(torch_cuda):
     N.check(lib.pgx_normalize(0, C.c_void_p(dst.data_ptr()), 6, ldb, C.c_void_p(out.data_ptr()), 6, B, None))
     torch.cuda.synchronize()
     np.testing.assert_allclose(out.cpu().numpy(), (got / got.sum(axis=0)).T, rtol=1e-15)
+    # a leading dimension below 32 that is not a power of two (the header accepts any ldb >= B): the kernel tiles the
+    # batch by 16 here, so rows 16..19 must come from a second tile
+    B2, ldb2 = 20, 24
+    dst2 = torch.full((6, ldb2), -1.0, dtype=torch.float64, device="cuda")
+    N.check(lib.pgx_evidence_reduce(0, C.c_void_p(t_dev.data_ptr()), table.size, 2, arr([3, 2]), arr([40, 5]), 2,
+                                    arr([0, 1]), arr([10, 1]), arr([4, 5]), C.c_void_p(ev_dev.data_ptr()), 2,
+                                    C.c_void_p(dst2.data_ptr()), B2, ldb2, None))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(dst2.cpu().numpy()[:, :B2], got[:, :B2])
 
 
 def test_discrete_factor_algebra_vectors(torch_cuda):

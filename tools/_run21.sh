@@ -1,7 +1,7 @@
-for cfgx in "12000 8000" "6000 4000" "3000 2000" "1500 1000"; do
-  set -- $cfgx; wc=$1; mc=$2
-  echo "== wave_cycles $wc min_cycles $mc"
-  for cfg in "diabetes 2048" "munin 256"; do set -- $cfg
-    PGX_MM_WAVE_CYCLES=$wc PGX_MM_MIN_CYCLES=$mc timeout 200 python tools/launch_profile.py $1 $2 1 2>&1 | sed -n 2p
+for cfgx in "512 4" "256 4" "1024 4" "512 2" "512 8" "256 8" "1024 2"; do
+  set -- $cfgx; to=$1; btb=$2
+  echo "== TO cap $to btb $btb"
+  for cfg in "diabetes 2048" "munin 256" "pathfinder 16384"; do set -- $cfg
+    PGX_TILE_TO_CAP=$to PGX_TILE_BTB=$btb timeout 200 python tools/launch_profile.py $1 $2 1 2>&1 | sed -n 2p
   done
 done
