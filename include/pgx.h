@@ -72,8 +72,7 @@ extern "C" {
  * slower than the default on every model (profiles/r01_final_summary.md) and are retired; the numbers stay reserved. */
 
 #define PGX_OPT_STAGE 9        /* stepwise mode, matrix-product-shaped two-operand steps: 1 (default) the pipelined
-                                  TMA-staged tile kernel k_contract_mm (pgx_mm.cu) | 2 the first-generation staged
-                                  kernel (pgx_stage.cuh) | 0 the streaming kernel only */
+                                  shared-memory-staged tile kernel k_contract_mm (pgx_mm.cu) | 0 the streaming kernel only */
 #define PGX_OPT_MMA 10         /* k_contract_mm: fp64 tensor cores (DMMA m8n8k4) for steps whose first operand is a
                                   batch-invariant table, [M x K] . [K x (N . B)] (default 1; 0 = FMA consumers) */
 
@@ -147,10 +146,6 @@ int pgx_profile_steps(pgx_plan* plan, const int32_t* ev_states, void* out, void*
 int pgx_profile_launches(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
                          int64_t B, void* stream, float* launch_ms, int32_t cap_launches, int32_t* step_launch,
                          int32_t n_steps, int32_t* n_launches);
-
-/* Host only (no GPU needed): the tiling the staged GEMM-tile kernel (pgx_stage.cuh) would use for one step record
- * (layout in pgmpy_b200/plan.py). fields[12] = eligible, ax, ay, bx, by, ntx, nty, tiles, sc, swap, form, stage_elems. */
-int pgx_stage_pick(const int32_t* step_record, int32_t item_bytes, int32_t* fields, int64_t* smem_bytes);
 
 /* Host only (no GPU needed): how k_contract_mm (pgx_mm.cu) would run one step record: the step seen as Z matrix
  * products out_z[M, N] = P_z[M, K] Q_z[K, N] per evidence set. fields[24] = eligible, M, N, Z, K, lgTX, lgTY, TZ, lgKC,

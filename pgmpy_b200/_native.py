@@ -28,7 +28,6 @@ EXPORTS = (
     "pgx_run_batch_mpe",
     "pgx_profile_steps",
     "pgx_profile_launches",
-    "pgx_stage_pick",
     "pgx_mm_pick",
     "pgx_plan_set_option",
     "pgx_plan_get_info",
@@ -96,8 +95,6 @@ def load():
         i32p, C.c_int32, i32p,
     ]
     lib.pgx_profile_launches.restype = C.c_int
-    lib.pgx_stage_pick.argtypes = [i32p, C.c_int32, i32p, C.POINTER(C.c_int64)]
-    lib.pgx_stage_pick.restype = C.c_int
     lib.pgx_mm_pick.argtypes = [i32p, C.c_int32, C.c_int32, i32p, i32p, C.c_int64, C.POINTER(C.c_int64)]
     lib.pgx_mm_pick.restype = C.c_int
     lib.pgx_plan_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int64]

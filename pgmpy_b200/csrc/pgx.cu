@@ -24,7 +24,6 @@
 #include "../../include/pgx.h"
 #include "pgx_step.cuh"
 #include "pgx_fused.cuh"
-#include "pgx_stage.cuh"
 #include "pgx_mm.h"
 
 namespace {
@@ -700,129 +699,22 @@ struct LaunchGroup {
     int generic_step = -1;  // >= 0: one launch of the generic kernel for this step
     int first_item = 0, n_items = 0, n_blocks = 0, max_k = 0;
     size_t smem = 0;
-    bool stage = false;  // every step of the group goes to k_contract_stage (first-generation TMA-staged GEMM tiles)
     bool mm = false;     // every step of the group goes to k_contract_mm (pgx_mm.cu: pipelined matrix-product tiles)
     std::vector<int> step_ids;  // plan steps served by this launch (tracing: pgx_profile_launches)
 };
-
-// Host: can this step run on the staged GEMM-tile kernel, and with which tiling? (pgx_stage.cuh)
-static bool pick_stage(const int32_t* r, int64_t out_size, int64_t sum_size, size_t item_bytes, pgx::StageItem& it,
-                       size_t& smem_bytes) {
-    using namespace pgx;
-    const int A = r[0], S = r[1], K = r[2], flags = r[3];
-    if (K != 2 || flags != 0 || A < 1 || S < 1 || sum_size < 2 || sum_size > 4096 || out_size * sum_size < 2048) return false;
-    const int opw = OP_FIXED + A + S;
-    const int32_t* odims = r + STEP_FIXED;
-    const int32_t* ops = odims + A + S;
-    bool work[2];
-    for (int k = 0; k < 2; ++k) {
-        const int32_t* op = ops + k * opw;
-        if (op[3] != 0) return false;  // evidence-dependent operand: per-lane base, cannot be staged as rows
-        work[k] = (op[0] & 0xFF) == 1;
-    }
-    auto type_of = [&](int k, int ax, int ay) {
-        const int32_t* op = ops + k * opw;
-        return (op[OP_FIXED + ax] ? 1 : 0) | ((ay >= 0 && op[OP_FIXED + ay]) ? 2 : 0);
-    };
-    auto cnt = [](int t) { return t == 0 ? 1 : (t == 3 ? 16 : 4); };
-    // best (ax, ay, operand order): fewest shared-memory loads per useful multiply-add of a 4 x 4 register block
-    double best = 1e30;
-    int b_ax = -1, b_ay = -1, b_swap = 0, b_form = 0;
-    for (int ax = 0; ax < A; ++ax) {
-        if (odims[ax] < 2) continue;
-        for (int ay = -1; ay < A; ++ay) {
-            if (ay == ax || (ay >= 0 && odims[ay] < 2)) continue;
-            for (int sw = 0; sw < 2; ++sw) {
-                const int tp = type_of(sw, ax, ay), tq = type_of(1 - sw, ax, ay);
-                const int form = tp * 4 + tq;
-                if (!(form == 6 || form == 7 || form == 3 || form == 1 || form == 5)) continue;
-                if (ay < 0 && form != 1 && form != 5) continue;
-                const int ux = odims[ax] < 4 ? odims[ax] : 4;
-                const int uy = ay >= 0 ? (odims[ay] < 4 ? odims[ay] : 4) : 1;
-                const double loads = ay >= 0 ? cnt(tp) + cnt(tq) : (tp ? 4 : 1) + (tq ? 4 : 1);
-                // the math itself also takes issue slots for the padded block (16 or 4 multiply-adds)
-                const double score = (loads + 0.25 * (ay >= 0 ? 16 : 4)) / (ux * uy);
-                if (score < best) {
-                    best = score;
-                    b_ax = ax;
-                    b_ay = ay;
-                    b_swap = sw;
-                    b_form = form;
-                }
-            }
-        }
-    }
-    if (b_ax < 0 || best > 1.5) return false;  // the streaming kernel spends 2 loads per multiply-add
-    const int tp = b_form >> 2, tq = b_form & 3;
-    const int dX = odims[b_ax], dY = b_ay >= 0 ? odims[b_ay] : 1;
-    int64_t n_other = 1;
-    for (int a = 0; a < A; ++a)
-        if (a != b_ax && a != b_ay) n_other *= odims[a];
-    // register blocks per tile: fewest padded outputs + staged rows
-    static const int cand[][2] = {{2, 4}, {4, 2}, {2, 2}, {1, 4}, {4, 1}, {1, 8}, {8, 1}, {1, 2}, {2, 1}, {1, 1}, {2, 3}, {3, 2}, {1, 3}, {3, 1}, {1, 6}, {6, 1}};
-    double bc = 1e30;
-    int bx = 1, by = 1;
-    for (auto& c : cand) {
-        if (b_ay < 0 && c[1] != 1) continue;
-        const int64_t ntx = (dX + 4 * c[0] - 1) / (4 * c[0]), nty = (dY + 4 * c[1] - 1) / (4 * c[1]);
-        const int rows_p = work[b_swap] ? ((tp & 1) ? 4 * c[0] : 1) * ((tp & 2) ? 4 * c[1] : 1) : 0;
-        const int rows_q = work[1 - b_swap] ? ((tq & 1) ? 4 * c[0] : 1) * ((tq & 2) ? 4 * c[1] : 1) : 0;
-        const double cost = (double)(ntx * nty) * (1.5 * 16 * c[0] * c[1] + 8.0 * (rows_p + rows_q));
-        if (cost < bc) {
-            bc = cost;
-            bx = c[0];
-            by = c[1];
-        }
-    }
-    const int pitch_p = work[b_swap] ? 32 : 1, pitch_q = work[1 - b_swap] ? 32 : 1;
-    const int64_t slots_p = ((tp & 1) ? 4 * bx : 1) * ((tp & 2) ? 4 * by : 1);
-    const int64_t slots_q = ((tq & 1) ? 4 * bx : 1) * ((tq & 2) ? 4 * by : 1);
-    const int64_t per_s = slots_p * pitch_p + slots_q * pitch_q;  // elements per summed index
-    int64_t sc = (40 * 1024) / (per_s * (int64_t)item_bytes);
-    if (sc < 1) sc = 1;
-    if (sc > sum_size) sc = sum_size;
-    const int64_t n_chunks = (sum_size + sc - 1) / sc;
-    sc = (sum_size + n_chunks - 1) / n_chunks;
-    const int64_t p_elems = (slots_p * pitch_p * sc + 3) / 4 * 4;
-    const int64_t stage_elems = p_elems + (slots_q * pitch_q * sc + 3) / 4 * 4;
-    const int64_t rec_len = STEP_FIXED + A + S + 2 * opw;
-    smem_bytes = 128 + (size_t)(((rec_len + 3) & ~3) + ((2 * sum_size + 3) & ~3)) * 4 + 2 * (size_t)stage_elems * item_bytes;
-    if (smem_bytes > 200 * 1024) return false;
-    const int64_t ntx = (dX + 4 * bx - 1) / (4 * bx), nty = (dY + 4 * by - 1) / (4 * by);
-    const int64_t tiles = n_other * ntx * nty;
-    if (tiles > (1 << 24)) return false;
-    it.ax = b_ax;
-    it.ay = b_ay;
-    it.bx = bx;
-    it.by = by;
-    it.ntx = (int32_t)ntx;
-    it.nty = (int32_t)nty;
-    it.tiles = (int32_t)tiles;
-    it.sc = (int32_t)sc;
-    it.swap = b_swap;
-    it.form = b_form;
-    it.stage_elems = (int32_t)stage_elems;
-    it.p_elems = (int32_t)p_elems;
-    it.pad = 0;
-    if (const char* e = std::getenv("PGX_STAGE_DEBUG")) it.pad = std::atoi(e);  // tuning aid: 1 no math, 2 no copies
-    return true;
-}
 
 struct StepSchedule {
     int64_t B = 0;
     int step_kernel = 0, dtype_size = 0;
     std::vector<LaunchGroup> groups;
     TileItem* d_items = nullptr;
-    pgx::StageItem* d_stage_items = nullptr;
     pgx::MMItem* d_mm_items = nullptr;
     int32_t* d_mm_tabs = nullptr;
     void release() {
         if (d_items) cudaFree(d_items);
-        if (d_stage_items) cudaFree(d_stage_items);
         if (d_mm_items) cudaFree(d_mm_items);
         if (d_mm_tabs) cudaFree(d_mm_tabs);
         d_items = nullptr;
-        d_stage_items = nullptr;
         d_mm_items = nullptr;
         d_mm_tabs = nullptr;
     }
@@ -867,8 +759,8 @@ struct pgx_plan {
     std::vector<StepSchedule> schedules;
     cudaStream_t cap_stream = nullptr;
     int last_graph = 0;
-    int stage = 1;        // matrix-product-shaped two-operand steps: 1 k_contract_mm (default), 2 first-generation
-                          // k_contract_stage, 0 streaming kernel only (PGX_OPT_STAGE)
+    int stage = 1;        // matrix-product-shaped two-operand steps: 1 k_contract_mm (default), 0 streaming kernel only
+                          // (PGX_OPT_STAGE)
     int mma = 1;          // fp64 tensor cores (DMMA) for steps whose P operand is batch invariant (PGX_OPT_MMA)
     int batch_levels = 1; // share one launch among the tile-eligible steps of a dependency level
     cudaEvent_t* prof_events = nullptr;  // set only inside pgx_profile_steps
@@ -1088,7 +980,7 @@ int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
         case PGX_OPT_STAGE:
         case PGX_OPT_MMA:
             if (option == PGX_OPT_STAGE) {
-                if (value < 0 || value > 2) return fail(PGX_ERR_INVALID, "stage must be 0, 1 or 2");
+                if (value < 0 || value > 1) return fail(PGX_ERR_INVALID, "stage must be 0 or 1");
                 plan->stage = (int)value;
             } else {
                 plan->mma = value ? 1 : 0;
@@ -1128,7 +1020,7 @@ int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value) {
             int64_t n = 0;
             if (plan->last_mode == PGX_MODE_STEPWISE && plan->last_sched >= 0 && plan->last_sched < (int)plan->schedules.size())
                 for (const LaunchGroup& g : plan->schedules[plan->last_sched].groups)
-                    if (g.stage || g.mm) n += g.n_items;
+                    if (g.mm) n += g.n_items;
             *value = n;
             break;
         }
@@ -1261,9 +1153,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
             };
             // per dependency level: one group of tile steps, generic steps alone
             LaunchGroup cur;
-            // ... and one group of steps for the TMA-staged GEMM-tile kernel
-            LaunchGroup cur_stage;
-            std::vector<StageItem> stage_items, pending_stage;
+            // ... and one group of steps for the matrix-product tile kernel (pgx_mm.cu)
             LaunchGroup cur_mm;
             std::vector<MMItem> mm_items, pending_mm;
             std::vector<double> pending_mm_cost;
@@ -1273,13 +1163,6 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
             int cur_level = -1;
             auto flush_level = [&]() {
                 flush(cur);
-                if (cur_stage.n_items > 0) {
-                    cur_stage.first_item = (int)stage_items.size();
-                    stage_items.insert(stage_items.end(), pending_stage.begin(), pending_stage.end());
-                    pending_stage.clear();
-                    ns.groups.push_back(cur_stage);
-                }
-                cur_stage = LaunchGroup();
                 if (cur_mm.n_items > 0) {
                     // split every step's tiles into CTA-sized runs. One CTA per SM is resident (the stage ring takes the
                     // shared memory), so the launch gets a whole number of waves: `waves` x resident CTAs dealt to the steps in
@@ -1333,7 +1216,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                 const int32_t* srec = pl->pool.data() + s.rec_off;
                 if (s.level != cur_level || !pl->batch_levels) flush_level();
                 cur_level = s.level;
-                if (stage_on && pl->stage == 1) {
+                if (stage_on) {
                     MMChoice ch;
                     if (mm_pick(srec, sizeof(T), pl->mma != 0, ldb, ch) &&
                         (int64_t)ch.item.n_tiles * b_tiles < (1LL << 30) && mm_tabs.size() + ch.tabs.size() < (1u << 30)) {
@@ -1346,25 +1229,6 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                         cur_mm.n_items += 1;
                         cur_mm.smem = std::max(cur_mm.smem, ch.smem);
                         continue;
-                    }
-                }
-                if (stage_on && pl->stage == 2 && tile_ok) {
-                    StageItem sit;
-                    size_t sm = 0;
-                    if (pick_stage(srec, s.out_size, s.sum_size, sizeof(T), sit, sm)) {
-                        const int64_t n_blocks = (int64_t)sit.tiles * b_tiles;
-                        if ((int64_t)cur_stage.n_blocks + n_blocks < (1LL << 30)) {
-                            sit.rec_off = s.rec_off;
-                            sit.rec_len = s.rec_len;
-                            sit.blk_begin = cur_stage.n_blocks;
-                            pending_stage.push_back(sit);
-                            cur_stage.stage = true;
-                            cur_stage.step_ids.push_back((int)si);
-                            cur_stage.n_items += 1;
-                            cur_stage.n_blocks += (int)n_blocks;
-                            cur_stage.smem = std::max(cur_stage.smem, sm);
-                            continue;
-                        }
                     }
                 }
                 if (!tile_ok) {
@@ -1406,10 +1270,6 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                 PGX_CUDA(cudaMalloc((void**)&ns.d_items, items.size() * sizeof(TileItem)));
                 PGX_CUDA(cudaMemcpy(ns.d_items, items.data(), items.size() * sizeof(TileItem), cudaMemcpyHostToDevice));
             }
-            if (!stage_items.empty()) {
-                PGX_CUDA(cudaMalloc((void**)&ns.d_stage_items, stage_items.size() * sizeof(StageItem)));
-                PGX_CUDA(cudaMemcpy(ns.d_stage_items, stage_items.data(), stage_items.size() * sizeof(StageItem), cudaMemcpyHostToDevice));
-            }
             if (!mm_items.empty()) {
                 PGX_CUDA(cudaMalloc((void**)&ns.d_mm_items, mm_items.size() * sizeof(MMItem)));
                 PGX_CUDA(cudaMemcpy(ns.d_mm_items, mm_items.data(), mm_items.size() * sizeof(MMItem), cudaMemcpyHostToDevice));
@@ -1438,7 +1298,15 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                 k_scatter_inputs<T><<<in_blocks, 256, 0, qs>>>(d_inputs, soft, ws, B, ldb);
                 ++n;
             }
+            static const int prof_sync = std::getenv("PGX_PROFILE_SYNC") ? std::atoi(std::getenv("PGX_PROFILE_SYNC")) : 0;
             for (const LaunchGroup& g : sched->groups) {
+                if (evs && prof_sync) {  // tracing aid: let the previous launch (and its write-backs) drain first
+                    cudaStreamSynchronize(qs);
+                    if (prof_sync > 1) {  // ... and push its dirty lines out of L2 by reading the table head
+                        cudaMemsetAsync(ws_all, 0, 0, qs);
+                    }
+                    cudaEventRecord(evs[ev_idx], qs);
+                }
                 if (g.generic_step >= 0) {
                     const StepInfo& s = pl->steps[g.generic_step];
                     // generic kernel: consecutive entries per thread, as many as leave >= ~4 waves of CTAs on 148 SMs
@@ -1462,12 +1330,6 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                 } else if (g.mm) {
                     mm_launch(sizeof(T), sched->d_mm_items + g.first_item, g.n_items, g.n_blocks, g.smem, sched->d_mm_tabs, ws_all,
                               (uint32_t)ws_off0, B, (uint32_t)ldb, (int)b_tiles, qs);
-                } else if (g.stage) {
-                    if (g.smem > 48 * 1024)
-                        cudaFuncSetAttribute(k_contract_stage<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-                    k_contract_stage<T><<<(unsigned)g.n_blocks, 256, g.smem, qs>>>(pl->d_pool, sched->d_stage_items + g.first_item,
-                                                                                  g.n_items, ws_all, ws_all, (uint32_t)ws_off0, B,
-                                                                                  (uint32_t)ldb);
                 } else {
                     const TileItem* d_it = sched->d_items + g.first_item;
 #define PGX_LAUNCH_TILE(MK)                                                                                            \
@@ -1704,17 +1566,6 @@ int pgx_profile_launches(pgx_plan* plan, const int32_t* ev_states, void* out, vo
         launch_ms[g] = ms[g];
         for (int si : sc.groups[g].step_ids) step_launch[si] = (int32_t)g;
     }
-    return PGX_OK;
-}
-
-int pgx_stage_pick(const int32_t* step_record, int32_t item_bytes, int32_t* fields, int64_t* smem_bytes) {
-    if (!step_record || !fields || !smem_bytes || (item_bytes != 4 && item_bytes != 8)) return fail(PGX_ERR_INVALID, "bad argument");
-    pgx::StageItem it{};
-    size_t sm = 0;
-    const bool ok = pick_stage(step_record, ld_i64(step_record + 4), ld_i64(step_record + 6), (size_t)item_bytes, it, sm);
-    *smem_bytes = (int64_t)sm;
-    const int32_t f[12] = {ok ? 1 : 0, it.ax, it.ay, it.bx, it.by, it.ntx, it.nty, it.tiles, it.sc, it.swap, it.form, it.stage_elems};
-    for (int i = 0; i < 12; ++i) fields[i] = f[i];
     return PGX_OK;
 }
 

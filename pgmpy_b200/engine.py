@@ -94,8 +94,8 @@ class CompiledPlan:
         return {0: "stepwise", 1: "generic", 2: "tables-smem", 3: "tables-global"}[v]
 
     def set_stage(self, which=1):
-        """Matrix-product-shaped two-operand steps: 1/True the pipelined TMA-staged tile kernel k_contract_mm (default),
-        2 the first-generation staged kernel, 0/False the streaming kernel only."""
+        """Matrix-product-shaped two-operand steps: 1/True the pipelined shared-memory-staged tile kernel k_contract_mm
+        (default), 0/False the streaming kernel only."""
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_STAGE, int(which)))
 
     def set_mma(self, enabled: bool = True):

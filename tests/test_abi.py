@@ -83,36 +83,6 @@ def test_run_batch_argument_checks():
     assert lib.pgx_workspace_bytes(None, 10) == 0
 
 
-def test_stage_pick_finds_the_gemm_shape_of_a_two_operand_step():
-    """Host-only tile picker of the TMA-staged GEMM-tile kernel (pgx_stage_pick, no GPU needed): for
-    out[x, y] = sum_s P[x, s] * Q[s, y] it must choose form (X-only, Y-only) with the two output axes as tile axes."""
-    import ctypes as C
-
-    from pgmpy_b200 import _native as N
-    from pgmpy_b200.plan import PlanBuilder
-
-    card = {"x": 21, "y": 55, "s": 96}
-    b = PlanBuilder(card, [])
-    p0 = b.add_const(["x", "s"], np.ones((21, 96)))
-    q0 = b.add_const(["s", "y"], np.ones((96, 55)))
-    p = b.contract([p0], ["x", "s"])  # work tables (batch dependent in a real plan)
-    q = b.contract([q0], ["s", "y"])
-    out = b.contract([p, q], ["x", "y"])
-    b.emit(out, False)
-    plan = b.finalize()
-    pool = np.ascontiguousarray(plan.pool, dtype=np.int32)
-    rec_off = int(pool[pool[10] + plan.n_steps - 1])  # last step = the contraction
-    lib = N.load()
-    f = (C.c_int32 * 12)()
-    sm = C.c_int64()
-    rec = pool[rec_off:]
-    assert lib.pgx_stage_pick(rec.ctypes.data_as(C.POINTER(C.c_int32)), 8, f, C.byref(sm)) == 0
-    ok, ax, ay, bx, by, ntx, nty, tiles, sc, swap, form, stage_elems = list(f)
-    assert ok == 1 and {ax, ay} == {0, 1} and form == 1 * 4 + 2
-    assert 1 <= bx * by <= 8 and ntx * 4 * bx >= card["x" if ax == 0 else "y"] and 1 <= sc <= 96
-    assert 0 < sm.value <= 200 * 1024 and tiles == ntx * nty
-
-
 def _mm_pick(rec, item_bytes=8, allow_mma=1):
     import ctypes as C
 
