@@ -700,6 +700,7 @@ struct LaunchGroup {
     int first_item = 0, n_items = 0, n_blocks = 0, max_k = 0;
     size_t smem = 0;
     bool mm = false;     // every step of the group goes to k_contract_mm (pgx_mm.cu: pipelined matrix-product tiles)
+    int level = 0;       // dependency level of its steps: launches of one level are independent of each other
     std::vector<int> step_ids;  // plan steps served by this launch (tracing: pgx_profile_launches)
 };
 
@@ -758,6 +759,11 @@ struct pgx_plan {
     GraphEntry graph_candidate{};  // argument tuple of the last graph-cache miss (exec unused)
     std::vector<StepSchedule> schedules;
     cudaStream_t cap_stream = nullptr;
+    // launches of one dependency level are independent: the second one runs on an auxiliary stream (fork / join by events,
+    // captured as parallel branches of the CUDA graph), so the tail of one overlaps the body of the other
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int level_streams = 1;
     int last_graph = 0;
     int stage = 1;        // matrix-product-shaped two-operand steps: 1 k_contract_mm (default), 0 streaming kernel only
                           // (PGX_OPT_STAGE)
@@ -952,6 +958,9 @@ void pgx_plan_destroy(pgx_plan* plan) {
     for (GraphEntry& g : plan->graphs) cudaGraphExecDestroy(g.exec);
     for (StepSchedule& c : plan->schedules) c.release();
     if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
+    if (plan->aux_stream) cudaStreamDestroy(plan->aux_stream);
+    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    if (plan->ev_join) cudaEventDestroy(plan->ev_join);
     delete plan;
 }
 
@@ -1142,11 +1151,13 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
             std::vector<TileItem> items;
             const int o_per_warp = 32 >> bt_log2;
             std::vector<TileItem> pending;  // items of the open tile group of the current level
+            int cur_level = -1;
             auto flush = [&](LaunchGroup& g) {
                 if (g.n_items > 0) {
                     g.first_item = (int)items.size();
                     items.insert(items.end(), pending.begin(), pending.end());
                     pending.clear();
+                    g.level = cur_level;
                     ns.groups.push_back(g);
                 }
                 g = LaunchGroup();
@@ -1160,7 +1171,6 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
             std::vector<int32_t> mm_tabs;
             const bool stage_on = pl->stage && pl->step_kernel == 0 && bt_log2 == 5 &&
                                   ws_off0 + (size_t)pl->ws_entries * (size_t)ldb < (1ULL << 32) && pl->ws_entries < (1LL << 31);
-            int cur_level = -1;
             auto flush_level = [&]() {
                 flush(cur);
                 if (cur_mm.n_items > 0) {
@@ -1196,6 +1206,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                     mm_items.insert(mm_items.end(), pending_mm.begin(), pending_mm.end());
                     pending_mm.clear();
                     pending_mm_cost.clear();
+                    cur_mm.level = cur_level;
                     ns.groups.push_back(cur_mm);
                 }
                 cur_mm = LaunchGroup();
@@ -1236,6 +1247,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                     LaunchGroup g;
                     g.generic_step = (int)si;
                     g.n_items = 1;
+                    g.level = s.level;
                     g.step_ids.push_back((int)si);
                     ns.groups.push_back(g);
                     continue;
@@ -1289,6 +1301,11 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
         // 32-bit addressing needs every element index (table copy + work tables) below 2^32
         const bool idx32 = pl->step_kernel == 0 && ws_off0 + (size_t)pl->ws_entries * (size_t)ldb < (1ULL << 32) &&
                            pl->ws_entries < (1LL << 31);
+        if (pl->level_streams && !pl->aux_stream) {
+            PGX_CUDA(cudaStreamCreateWithFlags(&pl->aux_stream, cudaStreamNonBlocking));
+            PGX_CUDA(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+            PGX_CUDA(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+        }
         auto enqueue = [&](cudaStream_t qs) -> int {
             int n = 0;
             cudaEvent_t* evs = pl->prof_events;
@@ -1299,7 +1316,30 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                 ++n;
             }
             static const int prof_sync = std::getenv("PGX_PROFILE_SYNC") ? std::atoi(std::getenv("PGX_PROFILE_SYNC")) : 0;
-            for (const LaunchGroup& g : sched->groups) {
+            static const int knob_streams = std::getenv("PGX_LEVEL_STREAMS") ? std::atoi(std::getenv("PGX_LEVEL_STREAMS")) : 1;
+            const bool fork_levels = pl->level_streams && knob_streams && !evs && pl->aux_stream && pl->ev_fork && pl->ev_join;
+            const cudaStream_t main_q = qs;
+            int lvl = -1 << 30, k_in_level = 0;
+            bool forked = false;
+            const size_t n_groups = sched->groups.size();
+            for (size_t gi = 0; gi < n_groups; ++gi) {
+                const LaunchGroup& g = sched->groups[gi];
+                if (g.level != lvl) {
+                    if (forked) {  // join: the next level needs everything of this one
+                        cudaEventRecord(pl->ev_join, pl->aux_stream);
+                        cudaStreamWaitEvent(main_q, pl->ev_join, 0);
+                        forked = false;
+                    }
+                    lvl = g.level;
+                    k_in_level = 0;
+                    if (fork_levels && gi + 1 < n_groups && sched->groups[gi + 1].level == lvl) {
+                        cudaEventRecord(pl->ev_fork, main_q);  // = the previous level is complete
+                        cudaStreamWaitEvent(pl->aux_stream, pl->ev_fork, 0);
+                        forked = true;
+                    }
+                }
+                qs = (forked && (k_in_level & 1)) ? pl->aux_stream : main_q;
+                ++k_in_level;
                 if (evs && prof_sync) {  // tracing aid: let the previous launch (and its write-backs) drain first
                     cudaStreamSynchronize(qs);
                     if (prof_sync > 1) {  // ... and push its dirty lines out of L2 by reading the table head
@@ -1357,6 +1397,11 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                 ++n;
                 if (evs) cudaEventRecord(evs[++ev_idx], qs);
             }
+            if (forked) {
+                cudaEventRecord(pl->ev_join, pl->aux_stream);
+                cudaStreamWaitEvent(main_q, pl->ev_join, 0);
+            }
+            qs = main_q;
             if (pl->n_segs > 0) {
                 dim3 grid((unsigned)((B + 127) / 128), (unsigned)pl->n_segs);
                 k_emit<T><<<grid, 128, 0, qs>>>(pl->d_pool, pl->segs_off, ws, out, pl->out_elems, B, ldb);
