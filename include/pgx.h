@@ -76,6 +76,9 @@ extern "C" {
 #define PGX_OPT_MMA 10         /* k_contract_mm: fp64 tensor cores (DMMA m8n8k4) for steps whose first operand is a
                                   batch-invariant table, [M x K] . [K x (N . B)] (default 1; 0 = FMA consumers) */
 
+#define PGX_OPT_TC32 11        /* fp32 mode: steps whose first operand is a batch-invariant table with >= 32 rows run as a
+                                  TF32x3 GEMM on the tcgen05 tensor cores with TMEM accumulators (pgx_tc32.cu; default 1) */
+
 #define PGX_INFO_N_STEPS 1
 #define PGX_INFO_OUT_ELEMS 2
 #define PGX_INFO_WS_ENTRIES 3
@@ -85,6 +88,7 @@ extern "C" {
 #define PGX_INFO_LAST_VARIANT 7 /* which fused kernel ran (PGX_OPT_FUSED_KERNEL numbering), 0 if stepwise */
 #define PGX_INFO_LAST_GRAPH 9    /* 1 if the most recent stepwise run was a CUDA-graph replay */
 #define PGX_INFO_LAST_STAGED_STEPS 10 /* steps the most recent stepwise run sent to the TMA-staged GEMM-tile kernel */
+#define PGX_INFO_LAST_TC_STEPS 12 /* steps the most recent stepwise run sent to the tcgen05 kernel (fp32 mode) */
 #define PGX_INFO_IN_ELEMS 11    /* elements of one row of `soft` (0: the plan has no input tables) */
 #define PGX_INFO_N_LEVELS 8     /* dependency levels of the plan (0 when no offset tables were built) */
 

@@ -12,10 +12,12 @@ MODE_AUTO, MODE_STEPWISE, MODE_FUSED = 0, 1, 2
 OPT_MODE, OPT_FUSED_WARPS, OPT_USE_GRAPH, OPT_FUSED_KERNEL, OPT_STEP_KERNEL = 1, 2, 3, 4, 5
 OPT_STAGE = 9
 OPT_MMA = 10
+OPT_TC32 = 11
 INFO_N_STEPS, INFO_OUT_ELEMS, INFO_WS_ENTRIES, INFO_LAST_LAUNCHES, INFO_LAST_MODE, INFO_N_EV = 1, 2, 3, 4, 5, 6
 INFO_LAST_VARIANT, INFO_N_LEVELS, INFO_LAST_GRAPH = 7, 8, 9
 INFO_LAST_STAGED_STEPS = 10
 INFO_IN_ELEMS = 11
+INFO_LAST_TC_STEPS = 12
 FUSED_KERNELS = {"auto": 0, "generic": 1, "tables-smem": 2, "tables-global": 3}
 
 EXPORTS = (

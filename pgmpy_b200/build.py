@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpgx.so")
-SOURCES = [os.path.join(CSRC, "pgx.cu"), os.path.join(CSRC, "pgx_mm.cu")]
+SOURCES = [os.path.join(CSRC, "pgx.cu"), os.path.join(CSRC, "pgx_mm.cu"), os.path.join(CSRC, "pgx_tc32.cu")]
 OBJ_DIR = os.path.join(CSRC, "_obj")
 
 

@@ -700,6 +700,7 @@ struct LaunchGroup {
     int first_item = 0, n_items = 0, n_blocks = 0, max_k = 0;
     size_t smem = 0;
     bool mm = false;     // every step of the group goes to k_contract_mm (pgx_mm.cu: pipelined matrix-product tiles)
+    bool tc = false;     // every step of the group goes to k_contract_tc32 (pgx_tc32.cu: tcgen05 TF32x3, fp32 mode)
     int level = 0;       // dependency level of its steps: launches of one level are independent of each other
     std::vector<int> step_ids;  // plan steps served by this launch (tracing: pgx_profile_launches)
 };
@@ -768,6 +769,7 @@ struct pgx_plan {
     int stage = 1;        // matrix-product-shaped two-operand steps: 1 k_contract_mm (default), 0 streaming kernel only
                           // (PGX_OPT_STAGE)
     int mma = 1;          // fp64 tensor cores (DMMA) for steps whose P operand is batch invariant (PGX_OPT_MMA)
+    int tc32 = 1;         // fp32 mode: tcgen05 TF32x3 GEMM for steps whose P operand is batch invariant (PGX_OPT_TC32)
     int batch_levels = 1; // share one launch among the tile-eligible steps of a dependency level
     cudaEvent_t* prof_events = nullptr;  // set only inside pgx_profile_steps
     int step_kernel = 0;  // 0 = auto (tile-cooperative where possible), 1 = generic per-thread kernel only
@@ -988,11 +990,14 @@ int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
             return PGX_OK;
         case PGX_OPT_STAGE:
         case PGX_OPT_MMA:
+        case PGX_OPT_TC32:
             if (option == PGX_OPT_STAGE) {
                 if (value < 0 || value > 1) return fail(PGX_ERR_INVALID, "stage must be 0 or 1");
                 plan->stage = (int)value;
-            } else {
+            } else if (option == PGX_OPT_MMA) {
                 plan->mma = value ? 1 : 0;
+            } else {
+                plan->tc32 = value ? 1 : 0;
             }
             for (StepSchedule& c : plan->schedules) c.release();
             plan->schedules.clear();
@@ -1024,12 +1029,20 @@ int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value) {
         case PGX_INFO_LAST_VARIANT: *value = plan->last_variant; break;
         case PGX_INFO_LAST_GRAPH: *value = plan->last_graph; break;
         case PGX_INFO_IN_ELEMS: *value = plan->in_elems; break;
+        case PGX_INFO_LAST_TC_STEPS: {
+            int64_t n = 0;
+            if (plan->last_mode == PGX_MODE_STEPWISE && plan->last_sched >= 0 && plan->last_sched < (int)plan->schedules.size())
+                for (const LaunchGroup& g : plan->schedules[plan->last_sched].groups)
+                    if (g.tc) n += g.n_items;
+            *value = n;
+            break;
+        }
         case PGX_INFO_N_LEVELS: *value = plan->micro.ok ? plan->micro.n_levels : 0; break;
         case PGX_INFO_LAST_STAGED_STEPS: {
             int64_t n = 0;
             if (plan->last_mode == PGX_MODE_STEPWISE && plan->last_sched >= 0 && plan->last_sched < (int)plan->schedules.size())
                 for (const LaunchGroup& g : plan->schedules[plan->last_sched].groups)
-                    if (g.mm) n += g.n_items;
+                    if (g.mm || g.tc) n += g.n_items;
             *value = n;
             break;
         }
@@ -1139,13 +1152,13 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
         // launch schedule for this batch size: tile-eligible steps of one dependency level share a launch
         StepSchedule* sched = nullptr;
         for (StepSchedule& c : pl->schedules)
-            if (c.B == B && c.step_kernel == pl->step_kernel + 4 * pl->batch_levels + 32 * pl->stage + 128 * pl->mma &&
+            if (c.B == B && c.step_kernel == pl->step_kernel + 4 * pl->batch_levels + 32 * pl->stage + 128 * pl->mma + 256 * pl->tc32 &&
                 c.dtype_size == (int)sizeof(T))
                 sched = &c;
         if (!sched) {
             StepSchedule ns;
             ns.B = B;
-            ns.step_kernel = pl->step_kernel + 4 * pl->batch_levels + 32 * pl->stage + 128 * pl->mma;
+            ns.step_kernel = pl->step_kernel + 4 * pl->batch_levels + 32 * pl->stage + 128 * pl->mma + 256 * pl->tc32;
             const int64_t tile_b_tiles = b_tiles;
             ns.dtype_size = (int)sizeof(T);
             std::vector<TileItem> items;
@@ -1165,7 +1178,9 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
             // per dependency level: one group of tile steps, generic steps alone
             LaunchGroup cur;
             // ... and one group of steps for the matrix-product tile kernel (pgx_mm.cu)
-            LaunchGroup cur_mm;
+            LaunchGroup cur_mm, cur_tc;
+            std::vector<MMItem> pending_tc;
+            const int b_chunks = (int)((B + 127) / 128);
             std::vector<MMItem> mm_items, pending_mm;
             std::vector<double> pending_mm_cost;
             std::vector<int32_t> mm_tabs;
@@ -1210,6 +1225,23 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                     ns.groups.push_back(cur_mm);
                 }
                 cur_mm = LaunchGroup();
+                if (cur_tc.n_items > 0) {
+                    int nb = 0;
+                    for (MMItem& mi : pending_tc) {
+                        const int npc = mi.N < 16 ? mi.N : 16;  // n per CTA: the CPT slice is staged once per CTA
+                        mi.tiles_per_cta = npc;
+                        mi.n_ctas = mi.Z * b_chunks * ((mi.N + npc - 1) / npc);
+                        mi.blk_begin = nb;
+                        nb += mi.n_ctas;
+                    }
+                    cur_tc.n_blocks = nb;
+                    cur_tc.first_item = (int)mm_items.size();
+                    mm_items.insert(mm_items.end(), pending_tc.begin(), pending_tc.end());
+                    pending_tc.clear();
+                    cur_tc.level = cur_level;
+                    ns.groups.push_back(cur_tc);
+                }
+                cur_tc = LaunchGroup();
             };
             for (size_t si = 0; si < pl->steps.size(); ++si) {
                 const StepInfo& s = pl->steps[si];
@@ -1233,6 +1265,16 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                         (int64_t)ch.item.n_tiles * b_tiles < (1LL << 30) && mm_tabs.size() + ch.tabs.size() < (1u << 30)) {
                         ch.item.tab = (int32_t)mm_tabs.size();
                         mm_tabs.insert(mm_tabs.end(), ch.tabs.begin(), ch.tabs.end());
+                        if (sizeof(T) == 4 && pl->tc32 && B >= 128 && tc32_eligible(ch.item) &&
+                            (int64_t)ch.item.Z * b_chunks * ch.item.N < (1LL << 30)) {
+                            // fp32 mode, CPT x message: the tcgen05 tensor cores (TF32x3, TMEM accumulators)
+                            pending_tc.push_back(ch.item);
+                            cur_tc.tc = true;
+                            cur_tc.step_ids.push_back((int)si);
+                            cur_tc.n_items += 1;
+                            cur_tc.smem = std::max(cur_tc.smem, tc32_smem_bytes(ch.item));
+                            continue;
+                        }
                         pending_mm.push_back(ch.item);
                         pending_mm_cost.push_back(ch.cost);
                         cur_mm.mm = true;
@@ -1306,6 +1348,7 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
             PGX_CUDA(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
             PGX_CUDA(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
         }
+        const int b_chunks_rt = (int)((B + 127) / 128);
         auto enqueue = [&](cudaStream_t qs) -> int {
             int n = 0;
             cudaEvent_t* evs = pl->prof_events;
@@ -1367,6 +1410,9 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                     else
                         PGX_LAUNCH_STEP(MAX_OPS);
 #undef PGX_LAUNCH_STEP
+                } else if (g.tc) {
+                    tc32_launch(sched->d_mm_items + g.first_item, g.n_items, g.n_blocks, g.smem, sched->d_mm_tabs, ws_all,
+                                (uint32_t)ws_off0, B, (uint32_t)ldb, b_chunks_rt, qs);
                 } else if (g.mm) {
                     mm_launch(sizeof(T), sched->d_mm_items + g.first_item, g.n_items, g.n_blocks, g.smem, sched->d_mm_tabs, ws_all,
                               (uint32_t)ws_off0, B, (uint32_t)ldb, (int)b_tiles, qs);

@@ -60,4 +60,12 @@ bool mm_pick(const int32_t* rec, size_t item_bytes, bool allow_mma, int64_t ldb,
 cudaError_t mm_launch(size_t item_bytes, const MMItem* d_items, int n_items, int n_blocks, size_t smem, const int32_t* d_tabs,
                       void* ws_all, uint32_t ws_off0, int64_t B, uint32_t ldb, int b_tiles, cudaStream_t st);
 
+// fp32 mode, batch-invariant P: the same step on the tcgen05 tensor cores as a TF32x3 GEMM with TMEM accumulators
+// (pgx_tc32.cu). Uses the MMItem / offset tables of mm_pick; tiles_per_cta = n per CTA, one CTA per (z, 128 evidence
+// sets, run of n).
+bool tc32_eligible(const MMItem& it);
+size_t tc32_smem_bytes(const MMItem& it);
+cudaError_t tc32_launch(const MMItem* d_items, int n_items, int n_blocks, size_t smem, const int32_t* d_tabs, void* ws_all,
+                        uint32_t ws_off0, int64_t B, uint32_t ldb, int b_chunks, cudaStream_t st);
+
 }  // namespace pgx

@@ -102,6 +102,14 @@ class CompiledPlan:
         """fp64 tensor cores (DMMA) for k_contract_mm steps with a batch-invariant first operand (default on)."""
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_MMA, 1 if enabled else 0))
 
+    def set_tc32(self, enabled: bool = True):
+        """fp32 mode: CPT-times-message steps on the tcgen05 tensor cores (TF32x3, TMEM accumulators; default on)."""
+        N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_TC32, 1 if enabled else 0))
+
+    @property
+    def last_tc_steps(self) -> int:
+        return self.info(N.INFO_LAST_TC_STEPS)
+
     def set_graph(self, enabled: bool = True):
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_USE_GRAPH, 1 if enabled else 0))
 

@@ -908,3 +908,30 @@ def test_batched_mpe_with_traceback(torch_cuda):
     for r in range(5):
         for j, v in enumerate(cols):
             assert pred.iloc[r][v] == m.states[v][int(asg[r, j])]
+
+
+@pytest.mark.parametrize("name,B", [("diabetes", 160), ("munin", 130)])
+def test_fp32_tcgen05_path_matches(torch_cuda, name, B):
+    """fp32 mode, CPT-times-message steps with >= 32 CPT rows on k_contract_tc32 (tcgen05.mma kind::tf32 as a 3xTF32 split,
+    TMEM accumulators; needs B >= 128: one MMA row per evidence set) against the FFMA path of the same mode and against
+    the fp64 engine: 1e-5 on the posteriors, the fp32-mode criterion. The last chunk of 128 evidence sets is ragged."""
+    torch = torch_cuda
+    m = px.get_example_model(name)
+    ev_vars, states = sample_evidence(m, B, 8, seed=4)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars)
+    cp64 = _engine()(plan)
+    cp64.set_mode("stepwise")
+    want = cp64.run_host(states)
+    cp = _engine()(plan, dtype="float32")
+    cp.set_mode("stepwise")
+    cp.set_tc32(False)
+    ffma = cp.run_host(states)
+    assert cp.last_tc_steps == 0
+    cp.set_tc32(True)
+    got = cp.run_host(states)
+    assert cp.last_tc_steps > 0, "no step was routed to the tcgen05 kernel"
+    assert np.isfinite(got).all()
+    e_ffma, e_tc = float(np.max(np.abs(ffma - want))), float(np.max(np.abs(got - want)))
+    print(f"{name}: fp32 vs fp64 posteriors, max abs error: FFMA {e_ffma:.1e}, tcgen05 {e_tc:.1e}; {cp.last_tc_steps} tensor-core steps")
+    assert e_tc <= 1e-5 and e_ffma <= 1e-5  # the fp32-mode criterion of test_fp32_mode_larger_models
+    assert float(np.max(np.abs(got.astype(np.float64) - ffma))) <= 1e-5
