@@ -757,7 +757,7 @@ struct pgx_plan {
     int fused_warps = 0;  // 0 = auto
     int use_graph = 1;    // stepwise: replay the step sequence as a CUDA graph
     std::vector<GraphEntry> graphs;
-    GraphEntry graph_candidate{};  // argument tuple of the last graph-cache miss (exec unused)
+    std::vector<GraphEntry> graph_candidates;  // argument tuples of recent graph-cache misses (exec unused)
     std::vector<StepSchedule> schedules;
     cudaStream_t cap_stream = nullptr;
     // launches of one dependency level are independent: the second one runs on an auxiliary stream (fork / join by events,
@@ -1465,13 +1465,18 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                     g.dtype_size == (int)sizeof(T))
                     hit = &g;
             // capture + instantiate cost as much as dozens of direct passes (munin: thousands of nodes), so a tuple is
-            // captured only when it shows up a second time in a row of misses: callers that hand over fresh buffers on
+            // captured only when it shows up a second time among the recent misses: callers that hand over fresh buffers on
             // every call (out[lo:hi] slices, new evidence tensors) then never pay for a graph they will not replay
             const GraphEntry key{B, (const void*)ev, soft_v, out_v, ws_v, pl->step_kernel, (int)sizeof(T), 0, nullptr};
-            const GraphEntry& c = pl->graph_candidate;
-            const bool seen_before = c.B == key.B && c.ev == key.ev && c.soft == key.soft && c.out == key.out && c.ws == key.ws &&
-                                     c.step_kernel == key.step_kernel && c.dtype_size == key.dtype_size;
-            if (!hit && !seen_before) pl->graph_candidate = key;
+            bool seen_before = false;
+            for (const GraphEntry& c : pl->graph_candidates)
+                if (c.B == key.B && c.ev == key.ev && c.soft == key.soft && c.out == key.out && c.ws == key.ws &&
+                    c.step_kernel == key.step_kernel && c.dtype_size == key.dtype_size)
+                    seen_before = true;
+            if (!hit && !seen_before) {  // remember the last few misses (callers often alternate two or three buffer sets)
+                if (pl->graph_candidates.size() >= 8) pl->graph_candidates.erase(pl->graph_candidates.begin());
+                pl->graph_candidates.push_back(key);
+            }
             if (!hit && seen_before) {
                 if (!pl->cap_stream) PGX_CUDA(cudaStreamCreateWithFlags(&pl->cap_stream, cudaStreamNonBlocking));
                 cudaGraph_t graph = nullptr;
