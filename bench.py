@@ -41,7 +41,9 @@ def parse_args():
     ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
     ap.add_argument("--mode", default="auto", choices=["auto", "fused", "stepwise"])
     ap.add_argument("--fused-warps", type=int, default=0)
-    ap.add_argument("--fused-kernel", default="auto", choices=["auto", "generic", "tables-smem", "tables-global"])
+    ap.add_argument("--fused-kernel", default="auto", choices=["auto", "generic", "tables-smem", "tables-global", "specialized"])
+    ap.add_argument("--no-specialize", action="store_true",
+                    help="do not build the plan-specialised kernel (pgx_plan_specialize): time the table-driven kernel")
     ap.add_argument("--step-kernel", default="auto", choices=["auto", "generic", "tile64"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -371,6 +373,17 @@ def run_b200(args):
     # same evidence-variable set on every rank; each rank draws its own shard of evidence sets
     ev_vars, _ = sample_evidence(model, 1, k, seed=1)
     cp = bp.marginals_plan(ev_vars)
+    spec = None
+    if not args.no_specialize and args.mode != "stepwise" and args.fused_kernel in ("auto", "specialized"):
+        # one-off per evidence signature (NVRTC, seconds): the plan as straight-line sm_100a code
+        try:
+            t_spec = time.perf_counter()
+            spec = cp.specialize()
+            spec["specialize_s"] = round(time.perf_counter() - t_spec, 2)
+        except Exception as exc:  # divide/max plans, no libnvrtc: the table-driven kernel runs, and the line says why
+            if args.fused_kernel == "specialized":
+                raise
+            spec = {"specialized": False, "why": str(exc)[:200]}
     cp.set_mode(args.mode, args.fused_warps, args.fused_kernel, args.step_kernel)
     n_batches = 2
     shards = []
@@ -503,13 +516,14 @@ def run_b200(args):
         alg_bytes = cp.plan.algorithmic_bytes(B, itemsize)
         per_launch_ms = max_ms / args.steps
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-        fused = variant in ("generic", "tables-smem", "tables-global")
+        fused = variant in ("generic", "tables-smem", "tables-global", "specialized")
         roofline = {
             # the whole-plan kernel keeps its work tables in shared memory: HBM sees evidence in and posteriors out only
             # (`traffic`), so the binding resource is the SM's own load/store path and the per-level barriers; the
             # GB/s figure below is the notional one of SURVEY 8(d) (every operand counted as if it moved)
             "bound": "l1-lsu+barrier" if fused else "hbm",
-            "kernel": {"generic": "k_plan_fused", "tables-smem": "k_plan_fused2<smem>", "tables-global": "k_plan_fused2<global>"}.get(
+            "kernel": {"generic": "k_plan_fused", "tables-smem": "k_plan_fused2<smem>", "tables-global": "k_plan_fused2<global>",
+                       "specialized": "k_plan_spec (plan-specialised, NVRTC sm_100a)"}.get(
                 variant, "k_contract_tile32 / k_contract_mm (sum over the launch sequence)"),
             "achieved": achieved,
             "peak": peak,
@@ -525,8 +539,9 @@ def run_b200(args):
             try:
                 with open(prof) as f:
                     tr = json.load(f)
-                roofline["traffic"] = tr.get(f"{args.model}:{mode}:{B}")
-                roofline["ncu"] = tr.get(f"{args.model}:{mode}:{B}:ncu")
+                key = f"{args.model}:{'specialized' if variant == 'specialized' else mode}:{B}"
+                roofline["traffic"] = tr.get(key)
+                roofline["ncu"] = tr.get(key + ":ncu")
             except Exception:
                 pass
         line = {
@@ -545,7 +560,8 @@ def run_b200(args):
             "config": cfg,
             "engine": {"exec_mode": mode, "kernel_variant": variant, "distribute": cp.plan.meta.get("distribute"),
                        "factorized_potentials": bool(cp.plan.meta.get("factorized")),
-                       "l2": ("work tables live in shared memory; " if variant == "tables-smem" else "workspace %.0f MB streamed per step; " % (cp.workspace_bytes(B) / 1e6))
+                       "specialized_kernel": spec,
+                       "l2": ("work tables live in shared memory; " if variant in ("tables-smem", "specialized") else "workspace %.0f MB streamed per step; " % (cp.workspace_bytes(B) / 1e6))
                        + "posteriors written per step %.0f MB; two evidence batches alternate, no L2 flush needed for a kernel whose HBM traffic is write-only output" % (B * cp.out_elems * itemsize / 1e6)},
             "marginals_per_sec": value * len(cp.plan.segments),
             "roofline": roofline,

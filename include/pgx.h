@@ -63,7 +63,8 @@ extern "C" {
 #define PGX_OPT_FUSED_WARPS 2 /* warps cooperating on one row of 32 evidence sets in fused mode (1..32) */
 #define PGX_OPT_USE_GRAPH 3   /* stepwise mode: replay the launch sequence as a CUDA graph (0/1) */
 #define PGX_OPT_FUSED_KERNEL 4 /* 0 auto | 1 generic addressing | 2 offset tables + shared-memory work tables |
-                                  3 offset tables + global work tables */
+                                  3 offset tables + global work tables | 4 the plan-specialised kernel
+                                  (pgx_plan_specialize; auto uses it whenever it has been built) */
 
 #define PGX_OPT_STEP_KERNEL 5  /* stepwise mode: 0 auto (tile-cooperative kernel, 32-bit addressing) | 1 generic only |
                                   2 tile-cooperative kernel with 64-bit addressing */
@@ -91,6 +92,12 @@ extern "C" {
 #define PGX_INFO_LAST_TC_STEPS 12 /* steps the most recent stepwise run sent to the tcgen05 kernel (fp32 mode) */
 #define PGX_INFO_IN_ELEMS 11    /* elements of one row of `soft` (0: the plan has no input tables) */
 #define PGX_INFO_N_LEVELS 8     /* dependency levels of the plan (0 when no offset tables were built) */
+#define PGX_INFO_SPECIALIZED 13 /* 1 after a successful pgx_plan_specialize */
+#define PGX_INFO_SPEC_REGS 14   /* registers per thread / dynamic shared memory / NVRTC+load time of the specialised kernel */
+#define PGX_INFO_SPEC_SMEM 15
+#define PGX_INFO_SPEC_COMPILE_MS 16
+#define PGX_INFO_SPEC_LOADS 17  /* loads and fp instructions the generator emitted per row of 32 evidence sets */
+#define PGX_INFO_SPEC_FLOPS 18
 
 typedef struct pgx_plan pgx_plan; /* opaque */
 
@@ -159,6 +166,20 @@ int pgx_profile_launches(pgx_plan* plan, const int32_t* ev_states, void* out, vo
  * soffQ[K] again in work-table elements (x ldb; ldb = 1 in this host-only call, and 0 for a batch-invariant P). */
 int pgx_mm_pick(const int32_t* step_record, int32_t item_bytes, int32_t allow_mma, int32_t* fields, int32_t* tabs,
                 int64_t tabs_cap, int64_t* n_tabs);
+
+/* Plan-specialised whole-plan kernel (pgx_spec.cu). The per-query control flow the reference interprets in Python on
+ * every call (ExactInference.py:141-244, :770-895) is, for one evidence signature, a fixed list of multiply-adds:
+ * pgx_plan_specialize writes it out as straight-line CUDA C for sm_100a (one warp = 32 evidence sets, work tables in
+ * the warp's shared memory, batch-invariant CPT entries as immediates), compiles it with NVRTC (dlopen'ed libnvrtc;
+ * PGX_ERR_UNSUPPORTED when absent or when the plan has divide / max steps, input tables or more than 120 000 product
+ * terms) and loads it; later pgx_run_batch calls use it (PGX_INFO_LAST_VARIANT = 4). The table blob must not change
+ * afterwards. Costs seconds: worth it from ~10^8 evidence sets per plan.
+ * pgx_spec_source: host only, no GPU: the generated source (compile = 0), or compile it too (1; 2 = return the cubin
+ * instead of the source). desc->table_blob is a HOST pointer here. Returns the byte count (buf receives at most cap
+ * bytes), or < 0 with the reason in buf. stats8 = product terms, terms kept (non-zero coefficient), loads, fp
+ * instructions, work entries, shared-memory bytes, compile ms, cubin bytes. */
+int pgx_plan_specialize(pgx_plan* plan);
+int64_t pgx_spec_source(const pgx_plan_desc* desc, int32_t compile, char* buf, int64_t cap, int64_t* stats8);
 
 int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value);
 int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value);

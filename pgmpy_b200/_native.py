@@ -18,7 +18,8 @@ INFO_LAST_VARIANT, INFO_N_LEVELS, INFO_LAST_GRAPH = 7, 8, 9
 INFO_LAST_STAGED_STEPS = 10
 INFO_IN_ELEMS = 11
 INFO_LAST_TC_STEPS = 12
-FUSED_KERNELS = {"auto": 0, "generic": 1, "tables-smem": 2, "tables-global": 3}
+INFO_SPECIALIZED, INFO_SPEC_REGS, INFO_SPEC_SMEM, INFO_SPEC_COMPILE_MS, INFO_SPEC_LOADS, INFO_SPEC_FLOPS = 13, 14, 15, 16, 17, 18
+FUSED_KERNELS = {"auto": 0, "generic": 1, "tables-smem": 2, "tables-global": 3, "specialized": 4}
 
 EXPORTS = (
     "pgx_plan_create",
@@ -31,6 +32,8 @@ EXPORTS = (
     "pgx_profile_steps",
     "pgx_profile_launches",
     "pgx_mm_pick",
+    "pgx_plan_specialize",
+    "pgx_spec_source",
     "pgx_plan_set_option",
     "pgx_plan_get_info",
     "pgx_evidence_reduce",
@@ -99,6 +102,10 @@ def load():
     lib.pgx_profile_launches.restype = C.c_int
     lib.pgx_mm_pick.argtypes = [i32p, C.c_int32, C.c_int32, i32p, i32p, C.c_int64, C.POINTER(C.c_int64)]
     lib.pgx_mm_pick.restype = C.c_int
+    lib.pgx_plan_specialize.argtypes = [C.c_void_p]
+    lib.pgx_plan_specialize.restype = C.c_int
+    lib.pgx_spec_source.argtypes = [C.POINTER(PlanDesc), C.c_int32, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.pgx_spec_source.restype = C.c_int64
     lib.pgx_plan_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
     lib.pgx_plan_set_option.restype = C.c_int
     lib.pgx_plan_get_info.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]

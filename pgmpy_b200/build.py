@@ -7,7 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpgx.so")
-SOURCES = [os.path.join(CSRC, "pgx.cu"), os.path.join(CSRC, "pgx_mm.cu"), os.path.join(CSRC, "pgx_tc32.cu")]
+SOURCES = [os.path.join(CSRC, "pgx.cu"), os.path.join(CSRC, "pgx_mm.cu"), os.path.join(CSRC, "pgx_tc32.cu"),
+           os.path.join(CSRC, "pgx_spec.cu")]
 OBJ_DIR = os.path.join(CSRC, "_obj")
 
 
@@ -54,7 +55,7 @@ def build_native(force=False, verbose=False):
         log += so + se
         if p.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + so + se)
-    res = subprocess.run([nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [o for o, _ in procs],
+    res = subprocess.run([nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [o for o, _ in procs] + ["-ldl"],
                          capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)

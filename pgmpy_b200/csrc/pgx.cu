@@ -24,6 +24,7 @@
 #include "../../include/pgx.h"
 #include "pgx_step.cuh"
 #include "pgx_fused.cuh"
+#include "pgx_spec.h"
 #include "pgx_mm.h"
 
 namespace {
@@ -749,6 +750,8 @@ struct pgx_plan {
     // table-driven fused kernel (pgx_fused.cuh)
     pgx::MicroInfo micro;
     int32_t* d_micro = nullptr;
+    // plan-specialised kernel (pgx_spec.cu), built on request by pgx_plan_specialize
+    pgx::SpecKernel* spec = nullptr;
     // max-product traceback descriptor (pgx_plan_set_trace)
     int32_t* d_trace = nullptr;
     int trace_cols = 0;
@@ -956,6 +959,7 @@ void pgx_plan_destroy(pgx_plan* plan) {
     if (!plan) return;
     if (plan->d_pool) cudaFree(plan->d_pool);
     if (plan->d_micro) cudaFree(plan->d_micro);
+    pgx::pgx_spec_destroy(plan->spec);
     if (plan->d_trace) cudaFree(plan->d_trace);
     for (GraphEntry& g : plan->graphs) cudaGraphExecDestroy(g.exec);
     for (StepSchedule& c : plan->schedules) c.release();
@@ -972,6 +976,21 @@ size_t pgx_workspace_bytes(const pgx_plan* plan, int64_t B) {
     // head: room for a copy of the batch-invariant tables (32-bit-addressed step kernel); then the work tables
     const size_t head = ((size_t)plan->table_entries + 31) / 32 * 32;
     return (head + (size_t)plan->ws_entries * (size_t)pgx_batch_ld(B)) * item;
+}
+
+int pgx_plan_specialize(pgx_plan* plan) {
+    if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+    if (plan->spec) return PGX_OK;
+    if (plan->d_trace) return fail(PGX_ERR_UNSUPPORTED, "max-product plans are not specialised");
+    const size_t elem = plan->dtype == PGX_F64 ? 8 : 4;
+    std::vector<unsigned char> host((size_t)plan->table_entries * elem + 8);
+    if (plan->table_entries > 0) PGX_CUDA(cudaMemcpy(host.data(), plan->blob, (size_t)plan->table_entries * elem, cudaMemcpyDeviceToHost));
+    std::string why;
+    int warps = PGX_SPEC_DEFAULT_WARPS;
+    if (const char* e = std::getenv("PGX_SPEC_WARPS")) warps = std::max(1, std::atoi(e));  // tuning knob
+    plan->spec = pgx::pgx_spec_build(plan->pool.data(), (int64_t)plan->pool.size(), host.data(), plan->table_entries, plan->dtype, why, warps);
+    if (!plan->spec) return fail(PGX_ERR_UNSUPPORTED, "plan not specialised: " + why);
+    return PGX_OK;
 }
 
 int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
@@ -1009,7 +1028,7 @@ int pgx_plan_set_option(pgx_plan* plan, int32_t option, int64_t value) {
             plan->step_kernel = (int)value;
             return PGX_OK;
         case PGX_OPT_FUSED_KERNEL:
-            if (value < 0 || value > 3) return fail(PGX_ERR_INVALID, "fused kernel must be 0..3");
+            if (value < 0 || value > 4) return fail(PGX_ERR_INVALID, "fused kernel must be 0..4");
             plan->fused_kernel = (int)value;
             return PGX_OK;
         default:
@@ -1038,6 +1057,12 @@ int pgx_plan_get_info(const pgx_plan* plan, int32_t what, int64_t* value) {
             break;
         }
         case PGX_INFO_N_LEVELS: *value = plan->micro.ok ? plan->micro.n_levels : 0; break;
+        case PGX_INFO_SPECIALIZED: *value = plan->spec ? 1 : 0; break;
+        case PGX_INFO_SPEC_REGS: *value = plan->spec ? pgx::pgx_spec_stats(plan->spec).regs : 0; break;
+        case PGX_INFO_SPEC_SMEM: *value = plan->spec ? pgx::pgx_spec_stats(plan->spec).smem_bytes : 0; break;
+        case PGX_INFO_SPEC_COMPILE_MS: *value = plan->spec ? (int64_t)(pgx::pgx_spec_stats(plan->spec).compile_s * 1e3) : 0; break;
+        case PGX_INFO_SPEC_LOADS: *value = plan->spec ? pgx::pgx_spec_stats(plan->spec).loads : 0; break;
+        case PGX_INFO_SPEC_FLOPS: *value = plan->spec ? pgx::pgx_spec_stats(plan->spec).flops : 0; break;
         case PGX_INFO_LAST_STAGED_STEPS: {
             int64_t n = 0;
             if (plan->last_mode == PGX_MODE_STEPWISE && plan->last_sched >= 0 && plan->last_sched < (int)plan->schedules.size())
@@ -1076,7 +1101,16 @@ int run_typed(pgx_plan* pl, const int32_t* ev, const void* soft_v, void* out_v, 
                                                                                                          : PGX_MODE_STEPWISE;
     }
     int64_t launches = 0;
-    if (mode == PGX_MODE_FUSED && pl->micro.ok && pl->fused_kernel != 1) {
+    if (pl->fused_kernel == 4 && (!pl->spec || soft || pl->mode == PGX_MODE_STEPWISE))
+        return fail(PGX_ERR_UNSUPPORTED, "specialised kernel requested but not available for this call (pgx_plan_specialize)");
+    if (pl->spec && !soft && pl->mode != PGX_MODE_STEPWISE && (pl->fused_kernel == 0 || pl->fused_kernel == 4)) {
+        // plan-specialised straight-line kernel: whenever it has been built and the caller did not ask for another one
+        std::string err;
+        if (pgx::pgx_spec_launch(pl->spec, pl->blob, ev, out_v, B, (void*)st, err) != 0) return fail(PGX_ERR_CUDA, err);
+        mode = PGX_MODE_FUSED;
+        launches = 1;
+        pl->last_variant = 4;
+    } else if (mode == PGX_MODE_FUSED && pl->micro.ok && pl->fused_kernel != 1) {
         // table-driven kernel; work tables in shared memory when a row of 32 evidence sets fits
         const int64_t rows = (B + 31) / 32;
         const size_t ws_smem = (size_t)pl->ws_entries * 32 * sizeof(T);

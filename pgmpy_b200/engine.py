@@ -67,13 +67,28 @@ class CompiledPlan:
 
     # ---- options / info ----------------------------------------------------------------------
     def set_mode(self, mode: str = "auto", fused_warps: int = 0, fused_kernel: str = "auto", step_kernel: str = "auto"):
-        """mode: auto | stepwise | fused.  fused_kernel: auto | generic | tables-smem | tables-global.
+        """mode: auto | stepwise | fused.  fused_kernel: auto | generic | tables-smem | tables-global | specialized.
         step_kernel: auto (tile-cooperative, 32-bit addressing) | generic | tile64."""
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_STEP_KERNEL, {"auto": 0, "generic": 1, "tile64": 2}[step_kernel]))
         m = {"auto": N.MODE_AUTO, "stepwise": N.MODE_STEPWISE, "fused": N.MODE_FUSED}[mode]
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_MODE, m))
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_FUSED_WARPS, fused_warps))
         N.check(self.lib.pgx_plan_set_option(self.handle, N.OPT_FUSED_KERNEL, N.FUSED_KERNELS[fused_kernel]))
+
+    def specialize(self) -> dict:
+        """Build the plan-specialised kernel (pgx_plan_specialize): the plan's fixed multiply-add list as straight-line
+        sm_100a code, compiled with NVRTC (seconds). Later run() calls use it unless set_mode asks for another kernel.
+        Raises PgxError when the plan cannot be specialised (divide / max steps, soft-evidence inputs, too many product
+        terms, no libnvrtc). Returns the kernel's statistics."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.pgx_plan_specialize(self.handle))
+        return self.spec_info()
+
+    def spec_info(self) -> dict:
+        return {"specialized": bool(self.info(N.INFO_SPECIALIZED)), "registers": self.info(N.INFO_SPEC_REGS),
+                "smem_bytes": self.info(N.INFO_SPEC_SMEM), "compile_ms": self.info(N.INFO_SPEC_COMPILE_MS),
+                "loads_per_row": self.info(N.INFO_SPEC_LOADS), "fp_instr_per_row": self.info(N.INFO_SPEC_FLOPS)}
 
     def info(self, what: int) -> int:
         v = C.c_int64()
@@ -91,7 +106,7 @@ class CompiledPlan:
     @property
     def last_variant(self) -> str:
         v = self.info(N.INFO_LAST_VARIANT)
-        return {0: "stepwise", 1: "generic", 2: "tables-smem", 3: "tables-global"}[v]
+        return {0: "stepwise", 1: "generic", 2: "tables-smem", 3: "tables-global", 4: "specialized"}[v]
 
     def set_stage(self, which=1):
         """Matrix-product-shaped two-operand steps: 1/True the pipelined shared-memory-staged tile kernel k_contract_mm

@@ -60,6 +60,58 @@ def test_jt_all_marginals_vs_oracle(torch_cuda, name, mode, kernel, step_kernel)
                 assert cp.last_variant == "generic"
 
 
+@pytest.mark.parametrize("name", ["asia", "sachs", "child", "alarm"])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_specialized_kernel_vs_oracle(torch_cuda, name, dtype):
+    """The plan-specialised straight-line kernel (pgx_plan_specialize: NVRTC, sm_100a) against the numpy plan
+    interpreter on the same seeded evidence: fp64 1e-12, fp32 mode 1e-5; ragged batches (B not a multiple of 32)."""
+    m = px.get_example_model(name)
+    jt = JTStructure.from_model(m)
+    k = {"asia": 2, "sachs": 3, "child": 4}.get(name, 5)
+    ev_vars, states = sample_evidence(m, 1000, k, seed=7)
+    plan = compile_jt_plan(jt, ev_vars, distribute="ss")
+    cp = _engine()(plan, dtype=dtype)
+    info = cp.specialize()
+    assert info["specialized"] and info["registers"] > 0
+    want = run_plan(plan.pool, plan.const_blob, states)
+    for B in (1, 31, 33, 1000):
+        got = cp.run_host(states[:B])
+        assert cp.last_variant == "specialized" and cp.last_launches == 1
+        assert rel_err(got, want[:B]) <= (1e-12 if dtype == "float64" else 1e-5)
+    # the table-driven kernel is still there when asked for
+    cp.set_mode("fused", 0, "tables-smem")
+    got = cp.run_host(states[:64])
+    assert cp.last_variant == "tables-smem"
+    assert rel_err(got, want[:64]) <= (1e-12 if dtype == "float64" else 1e-5)
+
+
+def test_specialized_kernel_impossible_evidence_gives_nan(torch_cuda):
+    """P(e) = 0: values / values.sum() is NaN in the reference (DiscreteFactor.py:530); so it is here."""
+    m = px.get_example_model("asia")
+    jt = JTStructure.from_model(m)
+    plan = compile_jt_plan(jt, ("tub", "lung", "either"), distribute="ss")
+    cp = _engine()(plan)
+    cp.specialize()
+    names = {v: list(m.states[v]) for v in ("tub", "lung", "either")}
+    # either = "no" while tub = "yes": impossible (either is the deterministic OR of tub and lung)
+    st = np.array([[names["tub"].index("yes"), names["lung"].index("no"), names["either"].index("no")],
+                   [names["tub"].index("no"), names["lung"].index("no"), names["either"].index("no")]], dtype=np.int32)
+    got = cp.run_host(st)
+    want = run_plan(plan.pool, plan.const_blob, st)
+    assert np.isnan(got[0]).all() and np.isnan(want[0]).all()
+    assert rel_err(got[1:], want[1:]) <= 1e-12
+
+
+def test_specialize_refuses_divide_plans(torch_cuda):
+    m = px.get_example_model("alarm")
+    ev_vars, _ = sample_evidence(m, 1, 5, seed=1)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, distribute="divide")
+    cp = _engine()(plan)
+    with pytest.raises(Exception, match="not specialised"):
+        cp.specialize()
+    assert not cp.spec_info()["specialized"]
+
+
 def test_shared_memory_variant_is_selected_for_alarm(torch_cuda):
     m = px.get_example_model("alarm")
     ev_vars, states = sample_evidence(m, 4096, 5, seed=1)
