@@ -102,6 +102,20 @@ def test_specialized_kernel_impossible_evidence_gives_nan(torch_cuda):
     assert rel_err(got[1:], want[1:]) <= 1e-12
 
 
+def test_plan_is_specialized_automatically_after_enough_evidence_sets(torch_cuda):
+    m = px.get_example_model("child")
+    ev_vars, states = sample_evidence(m, 4096, 4, seed=3)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, distribute="ss")
+    cp = _engine()(plan)
+    cp.AUTO_SPECIALIZE_SETS = 6000
+    want = run_plan(plan.pool, plan.const_blob, states)
+    got1 = cp.run_host(states)
+    assert cp.last_variant != "specialized"
+    got2 = cp.run_host(states)  # 8192 sets seen: specialised before this run
+    assert cp.last_variant == "specialized"
+    assert rel_err(got1, want) <= 1e-12 and rel_err(got2, want) <= 1e-12
+
+
 def test_specialize_refuses_divide_plans(torch_cuda):
     m = px.get_example_model("alarm")
     ev_vars, _ = sample_evidence(m, 1, 5, seed=1)
