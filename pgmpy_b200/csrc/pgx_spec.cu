@@ -47,6 +47,7 @@ struct Op {
     std::vector<std::pair<int, int>> pairs;  // (evidence slot, stride)
     std::vector<int> ostr, sstr;
     int owner = -1;  // step whose output this work operand reads
+    bool div = false;
 };
 struct Step {
     int A = 0, S = 0, K = 0, flags = 0, level = 0;
@@ -118,8 +119,8 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
         Step& st = steps[si];
         st.A = r[0], st.S = r[1], st.K = r[2], st.flags = r[3], st.level = r[10];
         st.out_size = ld_i64(r + 4), st.sum_size = ld_i64(r + 6), st.out_off = ld_i64(r + 8);
-        if (st.flags != 0) {
-            why = "plan has max-reduce or divide steps";
+        if (st.flags & ~FLAG_DIV) {
+            why = "plan has max-reduce steps";
             return false;
         }
         const int opw = OP_FIXED + st.A + st.S;
@@ -132,10 +133,7 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
         for (int k = 0; k < st.K; ++k) {
             const int32_t* op = ops + k * opw;
             Op& o = st.ops[k];
-            if (op[0] & 0x100) {
-                why = "divisor operand";
-                return false;
-            }
+            o.div = (op[0] & 0x100) != 0;  // trailing operands of a divide step: out = (sum of products) / prod(divisors)
             o.work = (op[0] & 0xFF) == 1;
             o.base = ld_i64(op + 1);
             for (int j = 0; j < op[3]; ++j) o.pairs.push_back({r[op[4] + 2 * j], r[op[4] + 2 * j + 1]});
@@ -382,6 +380,8 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
             std::vector<std::string> f;
         };
         std::vector<std::vector<Term>> entry_terms;  // of the current group
+        std::vector<Term> entry_den;                 // divisor of each entry
+        std::vector<char> entry_has_den;
         std::vector<std::string> entry_out;  // where the entry goes: shared-memory reference or local variable
         std::map<std::string, std::string> group_loads;  // name -> load expression
         auto flush = [&]() {
@@ -429,11 +429,22 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
                     body += "      a += " + lit(konst, f32) + ";\n";
                     ++flops;
                 }
+                if (entry_has_den[i]) {
+                    const Term& d = entry_den[i];
+                    std::string de;
+                    for (const std::string& f : d.f) de += (de.empty() ? "" : " * ") + f, ++flops;
+                    if (de.empty() || d.coef != 1.0) de += (de.empty() ? "" : " * ") + lit(d.coef, f32);
+                    body += "      a = a / (" + de + ");\n";
+                    body += "      a = (a != a) ? (T)0 : a;\n";  // 0 / 0 -> 0
+                    flops += 12;
+                }
                 ue.s += "      {\n" + body;
                 ue.line("      %s = a; }", entry_out[i].c_str());
             }
             ue.line("    }");
             entry_terms.clear();
+            entry_den.clear();
+            entry_has_den.clear();
             entry_out.clear();
             group_loads.clear();
         };
@@ -455,14 +466,10 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
             }
             std::vector<Term> tl;
             std::map<std::string, std::string> need;
-            std::vector<int> sd(std::max(st.S, 1), 0);
-            for (int64_t s = 0; s < st.sum_size; ++s) {
-                Term t;
-                t.coef = 1.0;
-                for (int k = 0; k < st.K; ++k) {
-                    const Op& op = st.ops[k];
-                    int64_t e = ob[k];
-                    for (int a = 0; a < st.S; ++a) e += (int64_t)sd[a] * op.sstr[a];
+            Term cur_den{1.0, {}};
+            bool cur_has_den = false;
+            auto add_factor = [&](int k, int64_t e, Term& t) {
+                const Op& op = st.ops[k];
                     if (!op.work && op.pairs.empty()) {
                         t.coef *= cval(e);
                     } else if (op.work && op.pairs.empty() && pack && known.count({op.owner, e})) {
@@ -503,6 +510,18 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
                         need[name] = "__ldg(" + q[k] + " + " + std::to_string(e) + ")";
                         t.f.push_back(name);
                     }
+                            };
+
+            std::vector<int> sd(std::max(st.S, 1), 0);
+            for (int64_t s = 0; s < st.sum_size; ++s) {
+                Term t;
+                t.coef = 1.0;
+                for (int k = 0; k < st.K; ++k) {
+                    const Op& op = st.ops[k];
+                    int64_t e = ob[k];
+                    for (int a = 0; a < st.S; ++a) e += (int64_t)sd[a] * op.sstr[a];
+                    if (op.div) continue;
+                    add_factor(k, e, t);
                 }
                 ++stats.terms;
                 if (t.coef != 0.0) {
@@ -526,6 +545,27 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
                     }
                     v += t.coef;
                 }
+                Term den;
+                den.coef = 1.0;
+                bool has_den = false;
+                for (int k = 0; k < st.K; ++k)
+                    if (st.ops[k].div) add_factor(k, ob[k], den), has_den = true;
+                if (has_den && den.f.empty()) {
+                    // a constant divisor: 0 / 0 -> 0, x / 0 -> inf, like the reference's divide (DiscreteFactor.py:859-863)
+                    if (all_const) {
+                        v = (v == 0.0 && den.coef == 0.0) ? 0.0 : v / den.coef;
+                        tl.clear();
+                        Term c;
+                        c.coef = v;
+                        tl.push_back(c);
+                        has_den = false;
+                    }
+                } else if (has_den) {
+                    all_const = false;
+                }
+                if (!has_den) den = Term{1.0, {}};
+                cur_den = den;
+                cur_has_den = has_den;
                 if (all_const && pack) known[{si, st.out_off + o}] = f32 ? (double)(float)v : v, ++n_known;
             }
             // only the elements of kept terms are loaded
@@ -533,12 +573,17 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
             for (const Term& t : tl)
                 for (const std::string& f : t.f)
                     if (need.count(f)) used[f] = need[f];
+            for (const std::string& f : cur_den.f)
+                if (need.count(f)) used[f] = need[f];
             size_t merged = group_loads.size();
             for (auto& kv : used)
                 if (!group_loads.count(kv.first)) ++merged;
             if (merged > (size_t)cap && !entry_terms.empty()) flush();
             for (auto& kv : used) group_loads[kv.first] = kv.second;
             entry_terms.push_back(std::move(tl));
+            if (!cur_has_den) cur_den.coef = 1.0, cur_den.f.clear();
+            entry_den.push_back(cur_has_den ? cur_den : Term{1.0, {}});
+            entry_has_den.push_back(cur_has_den);
             if (in_smem[si]) {
                 entry_out.push_back(wsref(remap_obj(si, st.out_off) + o));
             } else {

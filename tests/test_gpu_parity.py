@@ -85,6 +85,20 @@ def test_specialized_kernel_vs_oracle(torch_cuda, name, dtype):
     assert rel_err(got, want[:64]) <= (1e-12 if dtype == "float64" else 1e-5)
 
 
+@pytest.mark.parametrize("name,distribute", [("alarm", "divide"), ("alarm", "belief"), ("hepar2", "auto"), ("win95pts", "auto")])
+def test_specialized_kernel_divide_plans_vs_oracle(torch_cuda, name, distribute):
+    """Belief-update plans (divide steps: sigma / mu with 0 / 0 -> 0, ExactInference.py:788-805) through the specialised
+    kernel; hepar2 and win95pts are the plans whose intermediates no longer fit registers (local-memory spills)."""
+    m = px.get_example_model(name)
+    ev_vars, states = sample_evidence(m, 300, 5, seed=9)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, distribute=distribute)
+    cp = _engine()(plan)
+    cp.specialize()
+    got = cp.run_host(states)
+    assert cp.last_variant == "specialized"
+    assert rel_err(got, run_plan(plan.pool, plan.const_blob, states)) <= 1e-12
+
+
 def test_specialized_kernel_impossible_evidence_gives_nan(torch_cuda):
     """P(e) = 0: values / values.sum() is NaN in the reference (DiscreteFactor.py:530); so it is here."""
     m = px.get_example_model("asia")
@@ -116,10 +130,10 @@ def test_plan_is_specialized_automatically_after_enough_evidence_sets(torch_cuda
     assert rel_err(got1, want) <= 1e-12 and rel_err(got2, want) <= 1e-12
 
 
-def test_specialize_refuses_divide_plans(torch_cuda):
+def test_specialize_refuses_max_product_plans(torch_cuda):
     m = px.get_example_model("alarm")
     ev_vars, _ = sample_evidence(m, 1, 5, seed=1)
-    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, distribute="divide")
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, reduce_max=True)
     cp = _engine()(plan)
     with pytest.raises(Exception, match="not specialised"):
         cp.specialize()

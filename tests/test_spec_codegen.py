@@ -38,14 +38,18 @@ def _host_run(src: bytes, tmp_path, blob, states, out_elems, dtype):
     return out
 
 
-@pytest.mark.parametrize("name,k,dtype", [("asia", 2, "float64"), ("child", 4, "float64"), ("alarm", 5, "float64"),
-                                          ("alarm", 0, "float64"), ("alarm", 5, "float32"), ("sachs", 3, "float64")])
-def test_generated_source_on_the_cpu_matches_the_plan_interpreter(name, k, dtype, tmp_path):
+@pytest.mark.parametrize("name,k,dtype,distribute", [
+    ("asia", 2, "float64", "ss"), ("child", 4, "float64", "ss"), ("alarm", 5, "float64", "ss"), ("alarm", 0, "float64", "ss"),
+    ("alarm", 5, "float32", "ss"), ("sachs", 3, "float64", "ss"),
+    # belief-update plans: divide steps (sigma / mu with 0 / 0 -> 0, ExactInference.py:788-805)
+    ("alarm", 5, "float64", "divide"), ("alarm", 5, "float64", "belief"), ("hepar2", 5, "float64", "auto"),
+    ("win95pts", 5, "float64", "auto")])
+def test_generated_source_on_the_cpu_matches_the_plan_interpreter(name, k, dtype, distribute, tmp_path):
     lib = N.load()
     m = px.get_example_model(name)
     B = 70  # two full rows of 32 and a ragged one
     ev_vars, states = sample_evidence(m, B, k, seed=11)
-    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, distribute="ss")
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, distribute=distribute)
     src, st = spec_source(lib, plan, dtype, 0)
     assert st["ws_entries"] <= plan.ws_entries and st["smem_bytes"] <= 226 * 1024
     assert st["loads"] < st["terms"] * 3  # distinct elements, not one load per factor of every term
@@ -69,10 +73,10 @@ def test_plans_the_generator_refuses():
     lib = N.load()
     m = px.get_example_model("alarm")
     ev_vars, _ = sample_evidence(m, 1, 5, seed=1)
-    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, distribute="divide")
-    with pytest.raises(RuntimeError, match="divide"):
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, reduce_max=True)
+    with pytest.raises(RuntimeError, match="max-reduce"):
         spec_source(lib, plan, "float64", 0)
     big = px.get_example_model("pathfinder")
     ev_vars, _ = sample_evidence(big, 1, 8, seed=1)
-    with pytest.raises(RuntimeError, match="too large|shared memory|divide"):
+    with pytest.raises(RuntimeError, match="too large|shared memory"):
         spec_source(lib, compile_jt_plan(JTStructure.from_model(big), ev_vars), "float64", 0)

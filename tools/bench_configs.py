@@ -93,7 +93,7 @@ def single_query_latency(name="alarm", n=200):
                       "bp_query_us": res["bp"], "ve_new_signature_ms": res["ve_cold_ms"], "bp_new_signature_ms": res["bp_cold_ms"]}), flush=True)
 
 
-def mixed_ve(name, batch=262144, n_sig=16):
+def mixed_ve(name, batch=262144, n_sig=16, specialize=False):
     """configs[2]: hepar2 / win95pts VE (min-fill order), mixed evidence: 16 observed sets per batch, equal shares."""
     m = px.get_example_model(name)
     ve = VariableElimination(m)
@@ -108,6 +108,8 @@ def mixed_ve(name, batch=262144, n_sig=16):
         ev_vars = [cand[i] for i in rng.choice(len(cand), 8, replace=False)]
         _, states = sample_evidence(m, per, 8, seed=100 + sgn, evidence_vars=ev_vars)
         cp = ve._plan([q], ev_vars, True, None)
+        if specialize:
+            cp.specialize()
         jobs.append((cp, torch.from_numpy(states).cuda(), torch.empty((per, cp.out_elems), dtype=torch.float64, device="cuda")))
     compile_s = time.perf_counter() - t0
 
@@ -118,6 +120,7 @@ def mixed_ve(name, batch=262144, n_sig=16):
     ms = timed(run)
     alg = sum(cp.plan.algorithmic_bytes(per) for cp, _, _ in jobs)
     print(json.dumps({"config": f"{name} VE single-variable posterior, mixed evidence ({n_sig} signatures x {per} sets)", "batch": per * n_sig,
+                      "variant": jobs[0][0].last_variant,
                       "plan_compile_s": round(compile_s, 2), "ms_per_batch": ms, "evidence_queries_per_sec": per * n_sig / ms * 1e3,
                       "alg_GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / PEAK}), flush=True)
 
@@ -141,6 +144,28 @@ def bp_all_marginals(name, batch, k=8, reps=3):
                       "workspace_GB": cp.workspace_bytes(batch) / 1e9}), flush=True)
 
 
+def spec_compare(name, batch=131072, k=5):
+    """Junction-tree all-marginals of a small model: the default kernel choice against the plan-specialised kernel."""
+    m = px.get_example_model(name)
+    bp = BeliefPropagation(m)
+    ev_vars, states = sample_evidence(m, batch, k, seed=1)
+    cp = bp.marginals_plan(ev_vars)
+    ev = torch.from_numpy(states).cuda()
+    out = torch.empty((batch, cp.out_elems), dtype=torch.float64, device="cuda")
+    ms0 = timed(lambda: cp.run(ev, out=out), warm=2, reps=5)
+    v0 = cp.last_variant
+    ref = out.clone()
+    t0 = time.perf_counter()
+    info = cp.specialize()
+    spec_s = time.perf_counter() - t0
+    ms1 = timed(lambda: cp.run(ev, out=out), warm=2, reps=10)
+    err = float(((out - ref).abs() / ref.abs().clamp_min(1e-300)).max())
+    print(json.dumps({"config": f"{name} junction-tree all-variable marginals, k = {k}", "batch": batch, "steps": cp.plan.n_steps,
+                      "distribute": cp.plan.meta.get("distribute"), "default_variant": v0, "ms_default": ms0, "ms_specialized": ms1,
+                      "variant": cp.last_variant, "speedup": ms0 / ms1, "evidence_queries_per_sec": batch / ms1 * 1e3,
+                      "specialize_s": round(spec_s, 2), "max_rel_diff_vs_default": err, "spec": info}), flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["alarm_ve", "mixed_ve", "large", "munin"]
     if "latency" in what:
@@ -151,6 +176,12 @@ if __name__ == "__main__":
     if "mixed_ve" in what:
         mixed_ve("hepar2")
         mixed_ve("win95pts")
+    if "mixed_ve_spec" in what:
+        mixed_ve("hepar2", specialize=True)
+        mixed_ve("win95pts", specialize=True)
+    if "spec" in what:
+        for nm in ("child", "alarm", "win95pts", "hepar2"):
+            spec_compare(nm)
     if "large" in what:
         bp_all_marginals("pathfinder", 16384)
         bp_all_marginals("diabetes", 2048)
