@@ -305,7 +305,7 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     // fewer than 255 registers when one warp runs the row (alarm: 9 CTAs x 168 registers + spills 0.080 ms, 8 x 254
     // 0.054 ms)
     int min_ctas = (int)std::max<size_t>(1, std::min<size_t>(G == 1 ? 8 : 32, (227 * 1024) / (smem + 1024)));
-    if (const char* e = std::getenv("PGX_SPEC_MINCTAS")) min_ctas = std::max(1, std::min(min_ctas, std::atoi(e)));  // tuning knob
+    if (const char* e = std::getenv("PGX_SPEC_MINCTAS")) min_ctas = std::max(1, std::min(32, std::atoi(e)));  // tuning knob
     em.line("extern \"C\" __global__ void __launch_bounds__(%d, %d) k_plan_spec(const T* __restrict__ cst, const int* __restrict__ ev,",
             32 * G, min_ctas);
     em.line("                                                            T* __restrict__ out, long long B) {");
@@ -326,6 +326,7 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
         std::string code;
         double cost;
         int level;
+        int step;
     };
     std::vector<Unit> units;
     int n_levels = 0;
@@ -451,7 +452,7 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
         auto close_unit = [&]() {
             flush();
             if (ue.s.empty()) return;
-            units.push_back({pre.s + ue.s + "  }\n", (double)(flops + loads - cost0) + 4.0, st.level});
+            units.push_back({pre.s + ue.s + "  }\n", (double)(flops + loads - cost0) + 4.0, st.level, si});
             ue.s.clear();
             cost0 = flops + loads;
         };
@@ -621,7 +622,7 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
         ue.line("  }");
         flops += 2 * n + 8;
         loads += n;
-        units.push_back({ue.s, 3.0 * n + 30.0, n_levels});
+        units.push_back({ue.s, 3.0 * n + 30.0, n_levels, n_steps + g});
     }
     // ---- the levels: units dealt to the warps of the row, largest first onto the least loaded warp; one CTA barrier
     // between levels (none at all when one warp runs the row: lane l only reads what lane l wrote)
@@ -629,6 +630,9 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     if (G == 1) {
         em.line("  if (PH(0)) {");
         em.s += local_decls;
+        // plan order (level by level). Emitting every step right before its first consumer (depth first from the
+        // outputs) was tried to shorten live ranges: ptxas then spills MORE (448 B of stack at 255 registers against
+        // none) — the collect messages have to stay alive until the distribute pass whatever the order is
         for (const Unit& u : units) em.s += u.code;
         em.line("  }");
         phase = 1;
