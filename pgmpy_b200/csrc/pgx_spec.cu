@@ -290,6 +290,28 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     em.line("#endif");
     em.line("#define PGX_WARPS %d", G);
     em.line("#define PH(p) (PGX_PHASE < 0 || PGX_PHASE == (p))");
+    // reciprocal of a segment sum: MUFU.RCP64H seed + three Newton steps, no slow-path subroutine (the sums that need
+    // one — subnormal — take pgx_renorm_slow; 0 -> NaN, which is what 0 * (1 / 0) has to give anyway)
+    if (!f32) {
+        em.line("#ifdef PGX_HOST_SIM");
+        em.line("static inline double pgx_rcp(double s) { return 1.0 / s; }");
+        em.line("#else");
+        em.line("__device__ __forceinline__ double pgx_rcp(double s) {");
+        em.line("  double r;");
+        em.line("  asm(\"rcp.approx.ftz.f64 %%0, %%1;\" : \"=d\"(r) : \"d\"(s));");
+        em.line("  r = fma(fma(-s, r, 1.0), r, r);");
+        em.line("  r = fma(fma(-s, r, 1.0), r, r);");
+        em.line("  r = fma(fma(-s, r, 1.0), r, r);");
+        em.line("  return r;");
+        em.line("}");
+        em.line("#endif");
+    } else {
+        em.line("#define pgx_rcp(s) (1.0f / (s))");
+    }
+    // rare path of the output normalisation (a sum so small that its reciprocal could overflow): one out-of-line copy
+    em.line("__device__ __noinline__ void pgx_renorm_slow(T* base, int lane, int e0, int n, T s) {");
+    em.line("  for (int i = 0; i < n; ++i) { T* p = base + (e0 + i) * P + (lane ^ ((e0 + i) & %d)); *p = *p / s; }", SWZ);
+    em.line("}");
     {
         std::string cm = "__device__ const int c_colmap[] = {";
         std::vector<int64_t> colmap(out_elems, 0);
@@ -338,6 +360,7 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     }
     // registers: G warps x min_ctas CTAs share 64 K registers
     const int reg_budget = std::min(255, (65536 / (32 * G * min_ctas)) & ~7);
+    const bool use_select = !(std::getenv("PGX_SPEC_SELECT") && std::atoi(std::getenv("PGX_SPEC_SELECT")) == 0);  // tuning knob
     int64_t kept = 0, loads = 0, flops = 0, n_known = 0, n_locals = 0;
     std::string local_decls;
     std::map<std::pair<int, int64_t>, double> known;  // (producing step, entry) -> value, for evidence-independent entries
@@ -489,7 +512,7 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
                         const std::string ed = "(" + q[k] + " + " + std::to_string(ne) + ")";
                         need[name] = "base[" + ed + " * P + (lane ^ (" + ed + " & " + std::to_string(SWZ) + "))]";
                         t.f.push_back(name);
-                    } else if (op.pairs.size() == 1 && ev_card[op.pairs[0].first] <= 4) {
+                    } else if (use_select && op.pairs.size() == 1 && ev_card[op.pairs[0].first] <= 4) {
                         // CPT entry indexed by ONE observed variable with few states: a select among immediates instead
                         // of a gather (the load/store path is the busy one, the ALU is not)
                         const int slot = op.pairs[0].first, card = ev_card[slot];
@@ -614,9 +637,9 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
         // values / values.sum() as values * (1 / sum): one division per segment (<= 1 ulp from the quotient);
         // 0 * inf = NaN like 0 / 0; where 1 / sum could overflow, divide
         ue.line("    if (s != (T)0 && (s < (T)0 ? -s : s) < (T)1e-30) {");
-        for (int i = 0; i < n; ++i) ue.line("      %s = v%d / s;", wsref(off + i).c_str(), i);
+        ue.line("      pgx_renorm_slow(base, lane, %lld, %d, s);", (long long)off, n);
         ue.line("    } else {");
-        ue.line("      const T r = (T)1 / s;");
+        ue.line("      const T r = pgx_rcp(s);");
         for (int i = 0; i < n; ++i) ue.line("      %s = v%d * r;", wsref(off + i).c_str(), i);
         ue.line("    }");
         ue.line("  }");

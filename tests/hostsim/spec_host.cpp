@@ -14,6 +14,8 @@ alignas(16) unsigned char smem_raw[256 * 1024];
 #define __launch_bounds__(...)
 #define __align__(x)
 #define __shared__
+#define PGX_HOST_SIM 1
+#define __noinline__
 #define __syncwarp()
 #define __syncthreads()
 static inline double __ldg(const double* p) { return *p; }
