@@ -438,6 +438,7 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     int min_ctas = (int)std::max<size_t>(1, std::min<size_t>(G == 1 ? std::max(1, 8 / R) : 32, (227 * 1024) / ((size_t)R * smem + 1024)));
     if (const char* e = std::getenv("PGX_SPEC_MINCTAS")) min_ctas = std::max(1, std::min(32, std::atoi(e)));  // tuning knob
     em.line("#define PGX_ROWS %d", R);
+    em.s += "@@SEGTAB@@";
     if (stage) {
         em.line("#ifndef PGX_HOST_SIM");
         em.line("__device__ __forceinline__ void pgx_bulk_store(void* dst, const void* src, unsigned bytes) {");
@@ -521,6 +522,7 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     if (const char* e = std::getenv("PGX_SPEC_ACC")) n_acc = std::max(1, std::min(4, std::atoi(e)));  // tuning knob
     const bool use_select = !(std::getenv("PGX_SPEC_SELECT") && std::atoi(std::getenv("PGX_SPEC_SELECT")) == 0);  // tuning knob
     int64_t kept = 0, loads = 0, flops = 0, n_known = 0, n_locals = 0;
+    std::string seg_table;  // normaliser table + slow path, spliced in front of the kernel
     std::string local_decls;
     std::map<std::pair<int, int64_t>, double> known;  // (producing step, entry) -> value, for evidence-independent entries
     // distinct elements held in registers per group of output entries
@@ -797,8 +799,55 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
         }
         close_unit();
     }
-    // ---- normalise the output segments in place (lane = evidence set): one more level of units
-    for (int g = 0; g < n_segs; ++g) {
+    // ---- normalise the output segments in place (lane = evidence set)
+    if (stage) {
+        // ONE branch per row instead of one per variable: the sums of all segments first, then either the straight-line
+        // reciprocal path or (some sum below 1e-30, zero or NaN: impossible evidence, underflow) an out-of-line loop that
+        // divides. With a branch per segment the instruction after each branch waited for its cache line (ncu source
+        // page: 32 MUFU.RCP64H held 18 % of all stall samples, all of them no_instructions; BSYNC another 9 %).
+        Emitter ue;
+        std::string tab;
+        int n_norm = 0;
+        ue.line("  { // normalise");
+        for (int g = 0; g < n_segs; ++g) {
+            const int32_t* sg = segs + g * SEG_WORDS;
+            if (!(sg[4] & SEG_NORMALIZE)) continue;
+            const int c0 = out_col0[seg_owner[g]], n = sg[2];
+            std::string sum = "so[" + std::to_string(c0) + "]";
+            for (int i = 1; i < n; ++i) sum += " + so[" + std::to_string(c0 + i) + "]";
+            ue.line("    const T s%d = %s;", g, sum.c_str());
+            tab += std::to_string(c0) + "," + std::to_string(n) + ",";
+            ++n_norm;
+        }
+        std::string ok = "true";
+        for (int g = 0; g < n_segs; ++g)
+            if (segs[g * SEG_WORDS + 4] & SEG_NORMALIZE) ok += " & (s" + std::to_string(g) + " >= (T)1e-30)";
+        ue.line("    if (%s) {", ok.c_str());
+        for (int g = 0; g < n_segs; ++g) {
+            const int32_t* sg = segs + g * SEG_WORDS;
+            if (!(sg[4] & SEG_NORMALIZE)) continue;
+            const int c0 = out_col0[seg_owner[g]], n = sg[2];
+            ue.line("      { const T r = pgx_rcp(s%d);", g);
+            for (int i = 0; i < n; ++i) ue.line("        so[%d] = so[%d] * r;", c0 + i, c0 + i);
+            ue.line("      }");
+            flops += 2 * n + 8;
+            loads += n;
+        }
+        ue.line("    } else {");
+        ue.line("      pgx_renorm_all_slow(so);");
+        ue.line("    }");
+        ue.line("  }");
+        if (n_norm > 0) {
+            seg_table = "__device__ const int c_segtab[] = {" + tab + "0};\n";
+            seg_table += "__device__ __noinline__ void pgx_renorm_all_slow(T* so) {\n";
+            seg_table += "  for (int g = 0; g < " + std::to_string(n_norm) + "; ++g) {\n";
+            seg_table += "    const int c0 = c_segtab[2 * g], n = c_segtab[2 * g + 1];\n";
+            seg_table += "    T s = (T)0;\n    for (int i = 0; i < n; ++i) s += so[c0 + i];\n";
+            seg_table += "    for (int i = 0; i < n; ++i) so[c0 + i] = so[c0 + i] / s;\n  }\n}\n";
+            units.push_back({ue.s, 400.0, n_levels, n_steps});
+        }
+    }
+    for (int g = 0; g < n_segs && !stage; ++g) {
         const int32_t* sg = segs + g * SEG_WORDS;
         if (!(sg[4] & SEG_NORMALIZE)) continue;
         const int64_t off = remap_obj(seg_owner[g], ld_i64(sg));
@@ -958,6 +1007,10 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     em.line("  }");
     em.line("}");
     em.line("#define PGX_N_PHASES %d", phase + 1);
+    }
+    {
+        const size_t at = em.s.find("@@SEGTAB@@");
+        if (at != std::string::npos) em.s.replace(at, 10, seg_table);
     }
     source = std::move(em.s);
     stats.terms = terms;
