@@ -471,35 +471,24 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
         for (int c = 0; c <= SWZ; ++c) em.line("  T* const x%d = base2 + (lane ^ %d);", c, c);
     if (stage) {
         em.line("  const long long n_rows = (B + 31) / 32;");
-        // the evidence of the NEXT row is fetched while this row computes: otherwise every row starts with a full DRAM
-        // latency in front of its first instruction (ncu: long_scoreboard 20 % of the stalls with 5 loads per row)
-        if (n_ev > 0) {
-            em.line("  long long pb = (long long)blockIdx.x * 32 + lane;");
-            em.line("  if (pb >= B) pb = B - 1;");
-            for (int j = 0; j < n_ev; ++j) em.line("  int pe%d = ev[pb * %d + %d];", j, n_ev, j);
-        }
+        // the evidence of the NEXT row is prefetched into L1 while this row computes (a register prefetch was tried: the
+        // five values get spilled at 255 registers and the spill store then waits for the load it was meant to hide)
         em.line("  for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {");
         em.line("  const long long row0 = row * 32;");
     } else {
         em.line("  const long long row0 = ((long long)blockIdx.x * %d + rowi) * 32;", R);
     }
-    if (stage) {
-        for (int j = 0; j < n_ev; ++j) {
-            em.line("  int e%d = pe%d;", j, j);
-            em.line("  e%d = e%d < 0 ? 0 : (e%d > %d ? %d : e%d);", j, j, j, ev_card[j] - 1, ev_card[j] - 1, j);
-        }
-        if (n_ev > 0) {
-            em.line("  pb = (row + gridDim.x) * 32 + lane;");
-            em.line("  if (pb >= B) pb = B - 1;");
-            for (int j = 0; j < n_ev; ++j) em.line("  pe%d = ev[pb * %d + %d];", j, n_ev, j);
-        }
-    } else {
-        em.line("  long long b = row0 + lane;");
-        em.line("  if (b >= B) b = B - 1;");
-        for (int j = 0; j < n_ev; ++j) {
-            em.line("  int e%d = ev[b * %d + %d];", j, n_ev, j);
-            em.line("  e%d = e%d < 0 ? 0 : (e%d > %d ? %d : e%d);", j, j, j, ev_card[j] - 1, ev_card[j] - 1, j);
-        }
+    em.line("  long long b = row0 + lane;");
+    em.line("  if (b >= B) b = B - 1;");
+    for (int j = 0; j < n_ev; ++j) {
+        em.line("  int e%d = ev[b * %d + %d];", j, n_ev, j);
+        em.line("  e%d = e%d < 0 ? 0 : (e%d > %d ? %d : e%d);", j, j, j, ev_card[j] - 1, ev_card[j] - 1, j);
+    }
+    if (stage && n_ev > 0) {
+        em.line("#ifndef PGX_HOST_SIM");
+        em.line("  { long long pb = (row + gridDim.x) * 32 + lane; if (pb >= B) pb = B - 1;");
+        em.line("    asm volatile(\"prefetch.global.L1 [%%0];\" :: \"l\"(ev + pb * %d)); }", n_ev);
+        em.line("#endif");
     }
     // A unit = a run of consecutive output entries of one step, the grain of work handed to a warp
     struct Unit {
@@ -888,7 +877,27 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
         int ui = 0;
         const bool skip_compute = std::getenv("PGX_SPEC_DEBUG_SKIP_COMPUTE") != nullptr;  // timing experiments only
         bool waited = !stage;
-        for (const Unit& u : units) {
+        // PGX_SPEC_DEFER=1: steps that only feed the output (marginals) emitted last, so that the previous row's bulk store
+        // — all CTAs issue theirs at about the same time, a 27 MB burst that takes ~5 us to drain — has the whole row
+        // to finish before the staging block is written again (ncu: the wait in front of the first output write holds
+        // 5 % of the stall samples). Measured: 0.0393 ms against 0.0300 — the marginals' operands then live to the
+        // end of the row and spill (592 B of stack). Off.
+        std::vector<Unit> ordered;
+        if (stage && std::getenv("PGX_SPEC_DEFER") && std::atoi(std::getenv("PGX_SPEC_DEFER")) != 0) {  // measured slower: off
+            std::vector<char> consumed(n_steps, 0);
+            for (const Step& st2 : steps)
+                for (const Op& o : st2.ops)
+                    if (o.work && o.owner >= 0) consumed[o.owner] = 1;
+            for (const Unit& u : units)
+                if (u.step < n_steps && !(in_smem[u.step] && !consumed[u.step])) ordered.push_back(u);
+            for (const Unit& u : units)
+                if (u.step < n_steps && in_smem[u.step] && !consumed[u.step]) ordered.push_back(u);
+            for (const Unit& u : units)
+                if (u.step >= n_steps) ordered.push_back(u);
+        } else {
+            ordered = units;
+        }
+        for (const Unit& u : ordered) {
             if (skip_compute) break;
             if (!waited && (u.step >= n_steps || in_smem[u.step])) {
                 // the previous row's bulk store reads the staging block: it must have finished before it is rewritten
