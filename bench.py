@@ -546,9 +546,9 @@ def run_b200(args):
                 "frac": io_bytes / (per_launch_ms * 1e-3) / 1e9 / peak,
                 "io_bytes_per_launch": int(io_bytes),
                 "survey_8d_step_formula": {"bytes_per_launch": int(alg_bytes), "GBps": achieved, "frac": achieved / peak},
-                "limiter": "not yet HBM: the compute part (0.037 of 0.043 ms; persistent CTAs, the TMA bulk store of a row drains under "
-                "the next row's compute) runs at about half the fp64 pipe's peak, 8 warps per SM at 255 registers; ncu: issue-active "
-                "29 %, fp64 pipe 35 %, stalls wait / no_instructions / long_scoreboard",
+                "limiter": "half way to HBM: the compute part (0.028 of 0.030 ms; persistent CTAs, the TMA bulk store of a row drains "
+                "under the next row's compute) keeps the fp64 pipe 56 % busy with 8 warps per SM at 255 registers; ncu: issue-active "
+                "45 %, stalls wait / selected / long_scoreboard",
                 "note": "achieved = (evidence in + posteriors out) / kernel time; traffic = ncu DRAM bytes of one launch (the rest of "
                 "the 95 MB of posteriors is still in the 126 MB L2 when the kernel ends). peak: " + peak_src,
             })
