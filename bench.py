@@ -372,18 +372,23 @@ def run_b200(args):
     bp = BeliefPropagation(model, dtype=args.dtype)
     # same evidence-variable set on every rank; each rank draws its own shard of evidence sets
     ev_vars, _ = sample_evidence(model, 1, k, seed=1)
-    cp = bp.marginals_plan(ev_vars)
     spec = None
-    if not args.no_specialize and args.mode != "stepwise" and args.fused_kernel in ("auto", "specialized"):
-        # one-off per evidence signature (NVRTC, seconds): the plan as straight-line sm_100a code
-        try:
-            t_spec = time.perf_counter()
-            spec = cp.specialize()
-            spec["specialize_s"] = round(time.perf_counter() - t_spec, 2)
-        except Exception as exc:  # divide/max plans, no libnvrtc: the table-driven kernel runs, and the line says why
-            if args.fused_kernel == "specialized":
-                raise
-            spec = {"specialized": False, "why": str(exc)[:200]}
+    want_spec = not args.no_specialize and args.mode != "stepwise" and args.fused_kernel in ("auto", "specialized")
+    # one-off per evidence signature (NVRTC, about a second): the plan variant with the fewest multiply-adds, as
+    # straight-line sm_100a code. Plans the generator refuses (max-product, soft evidence, too large) or a box without
+    # libnvrtc keep the table-driven kernel, and the line says so.
+    t_spec = time.perf_counter()
+    cp = bp.marginals_plan(ev_vars, specialize=want_spec)
+    if want_spec:
+        spec = cp.spec_info()
+        spec["plan_and_specialize_s"] = round(time.perf_counter() - t_spec, 2)
+        if not spec["specialized"]:
+            try:
+                cp.specialize()
+            except Exception as exc:
+                if args.fused_kernel == "specialized":
+                    raise
+                spec["why"] = str(exc)[:200]
     cp.set_mode(args.mode, args.fused_warps, args.fused_kernel, args.step_kernel)
     n_batches = 2
     shards = []

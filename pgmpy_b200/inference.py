@@ -504,12 +504,18 @@ class BeliefPropagation(_Inference):
     def get_sepset_beliefs(self):
         return self.sepset_beliefs
 
-    def _jt_plan(self, ev_vars, variables=None, emit_beliefs=False, soft_vars=()) -> CompiledPlan:
-        key = ("jt", tuple(ev_vars), None if variables is None else tuple(variables), emit_beliefs, tuple(soft_vars))
+    def _jt_plan(self, ev_vars, variables=None, emit_beliefs=False, soft_vars=(), specialize=False) -> CompiledPlan:
+        key = ("jt", tuple(ev_vars), None if variables is None else tuple(variables), emit_beliefs, tuple(soft_vars), bool(specialize))
         cp = self._plans.get(key)
         if cp is None:
-            plan = PL.compile_jt_plan(self._jt, ev_vars, variables, emit_beliefs=emit_beliefs, soft_vars=soft_vars)
+            plan = PL.compile_jt_plan(self._jt, ev_vars, variables, emit_beliefs=emit_beliefs, soft_vars=soft_vars,
+                                      objective="flops" if specialize else "bytes")
             cp = self._compile(plan)
+            if specialize:
+                try:
+                    cp.specialize()
+                except Exception:  # max / input plans, no libnvrtc: the other kernels serve the plan
+                    pass
             self._plans[key] = cp
         return cp
 
@@ -636,10 +642,13 @@ class BeliefPropagation(_Inference):
         soft = self._soft_rows(cp, virtual_evidence, int(ev_t.shape[0]) if ev_t is not None else None) if soft_vars else None
         return columns, cp.run_mpe(ev_t, soft)
 
-    def marginals_plan(self, evidence_vars, variables=None, soft_vars=()) -> CompiledPlan:
-        """Compiled all-marginals plan for one evidence-variable signature (bench / batched callers)."""
+    def marginals_plan(self, evidence_vars, variables=None, soft_vars=(), specialize=False) -> CompiledPlan:
+        """Compiled all-marginals plan for one evidence-variable signature (bench / batched callers).
+        `specialize=True`: the caller expects ~10^8 or more evidence sets on this signature — the plan variant with the
+        fewest multiply-adds is chosen (planner.plan_flops) and compiled into its own straight-line kernel right away
+        (CompiledPlan.specialize, about a second)."""
         self._check_query(variables or [], {v: None for v in evidence_vars}, allow_empty=True)
-        return self._jt_plan(list(evidence_vars), variables, soft_vars=tuple(soft_vars))
+        return self._jt_plan(list(evidence_vars), variables, soft_vars=tuple(soft_vars), specialize=specialize)
 
     def marginals_batch(self, evidence_vars, evidence_states, variables=None, virtual_evidence=None):
         """Posterior marginals of every unobserved variable (or `variables`) for B evidence sets:

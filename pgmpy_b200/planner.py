@@ -414,6 +414,24 @@ def plan_cost(plan: Plan) -> float:
     return nbytes / PlanBuilder.COST_BYTES_PER_NS + loads / PlanBuilder.COST_LOADS_PER_NS
 
 
+def plan_flops(plan: Plan) -> float:
+    """Multiply-adds per evidence set the plan-specialised kernel (csrc/pgx_spec.cu) would emit, roughly: per product
+    term one instruction per batch-dependent factor (the batch-invariant ones are folded into one immediate), a dozen
+    for a division. The objective for plans that will be specialised: that kernel keeps every message in registers,
+    so bytes — what plan_cost prices for the table-driven and step kernels — cost it nothing."""
+    ev = set(plan.ev_vars)
+    total = 0.0
+    for st in plan.steps:
+        ssz = 1
+        for v in st.sum_vars:
+            ssz *= plan.card[v]
+        n_dyn = sum(1 for t, d in st.operands if not d and (t.kind == 1 or any(v in ev for v in t.vars)))
+        n_const = sum(1 for t, d in st.operands if not d) - n_dyn
+        per_term = n_dyn if n_const else max(1, n_dyn - 1)
+        total += st.out.size * (ssz * max(1, per_term) + (12 if any(d for _, d in st.operands) else 0))
+    return total
+
+
 def compile_jt_plan(
     jt: JTStructure,
     evidence_vars: Sequence[Hashable] = (),
@@ -424,6 +442,7 @@ def compile_jt_plan(
     reduce_max: bool = False,
     factorized="auto",
     soft_vars: Sequence[Hashable] = (),
+    objective: str = "bytes",
 ) -> Plan:
     """Two-pass message passing on the rooted junction tree for one evidence-variable signature.
 
@@ -443,7 +462,8 @@ def compile_jt_plan(
     message before anything clique-sized is touched, and a clique without factors costs nothing at all.
     `distribute`: "ss" | "belief" | "divide" as above, "adaptive" = per clique, whichever of Shafer-Shenoy messages
     and materialised belief + marginalisation lattice the cost model prices lower; "auto" compiles the candidate
-    strategies and returns the cheapest plan."""
+    strategies and returns the cheapest plan — cheapest in modelled bytes + loads (`objective="bytes"`, the
+    table-driven and step kernels) or in multiply-adds (`objective="flops"`, plans that will be specialised)."""
     if (distribute == "auto" or factorized == "auto") and not emit_beliefs:
         # dense potentials + Shafer-Shenoy keeps the workspace smallest (messages only: fits shared memory for
         # alarm-class models); factor lists + per-clique choice wins on the big-clique models
@@ -461,6 +481,17 @@ def compile_jt_plan(
                 if d == "ss" and hub and distribute == "auto":
                     continue
                 cands.append(compile_jt_plan(jt, evidence_vars, variables, normalize, False, d, reduce_max, f, soft_vars))
+        if objective == "flops":
+            # ask the generator itself (host only, milliseconds): it folds evidence-independent messages and
+            # batch-invariant factors, which no formula over the step list sees (hepar2: Shafer-Shenoy around its
+            # 17-neighbour hub is 13 540 instructions after folding, the belief-update plan 20 041)
+            from .specialize import spec_flops
+
+            if hub and distribute == "auto":
+                cands += [compile_jt_plan(jt, evidence_vars, variables, normalize, False, "ss", reduce_max, f, soft_vars) for f in fz]
+            scored = [(spec_flops(p), i) for i, p in enumerate(cands)]
+            ok = [(c, i) for c, i in scored if c is not None]
+            return cands[min(ok)[1]] if ok else min(cands, key=plan_flops)
         cost = [plan_cost(p) for p in cands]
         best = min(range(len(cands)), key=lambda i: cost[i])
         # stay with the (dense, Shafer-Shenoy) candidate — smallest workspace, every step on the fused kernel's fast

@@ -15,21 +15,11 @@ from pgmpy_b200.evidence import sample_evidence
 from pgmpy_b200.planner import JTStructure, compile_jt_plan
 
 
+from pgmpy_b200.specialize import spec_source as _spec_source
+
+
 def spec_source(lib, plan, dtype="float64", compile=0):
-    pool = np.ascontiguousarray(plan.pool, dtype=np.int32)
-    blob = np.ascontiguousarray(plan.const_blob, dtype=np.float64 if dtype == "float64" else np.float32)
-    desc = N.PlanDesc(1, N.PGX_F64 if dtype == "float64" else N.PGX_F32, pool.ctypes.data_as(C.POINTER(C.c_int32)), pool.size,
-                      C.c_void_p(blob.ctypes.data), blob.size)
-    stats = (C.c_int64 * 8)()
-    lib.pgx_spec_source.restype = C.c_int64
-    lib.pgx_spec_source.argtypes = [C.POINTER(N.PlanDesc), C.c_int32, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]
-    cap = 64 << 20
-    buf = C.create_string_buffer(cap)
-    n = lib.pgx_spec_source(C.byref(desc), compile, buf, cap, stats)
-    if n < 0:
-        raise RuntimeError(f"pgx_spec_source: {n}: {buf.value.decode(errors='replace')[:2000]}")
-    keys = ["terms", "terms_kept", "loads", "flops", "ws_entries", "smem_bytes", "compile_ms", "cubin_bytes"]
-    return buf.raw[:n], dict(zip(keys, list(stats)))
+    return _spec_source(plan, dtype, compile, lib)
 
 
 if __name__ == "__main__":
