@@ -507,6 +507,7 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     }
     // registers: G warps x min_ctas CTAs share 64 K registers
     const int reg_budget = std::min(255, (65536 / (32 * G * min_ctas)) & ~7);
+    const bool factor_common = !(std::getenv("PGX_SPEC_FACTOR") && std::atoi(std::getenv("PGX_SPEC_FACTOR")) == 0);  // tuning knob
     int n_acc = PGX_SPEC_DEFAULT_ACC;
     if (const char* e = std::getenv("PGX_SPEC_ACC")) n_acc = std::max(1, std::min(4, std::atoi(e)));  // tuning knob
     const bool use_select = !(std::getenv("PGX_SPEC_SELECT") && std::atoi(std::getenv("PGX_SPEC_SELECT")) == 0);  // tuning knob
@@ -571,6 +572,29 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
                 bool first = true;
                 // n_acc > 1: the terms of an entry go round robin onto n_acc partial sums added at the end, which cuts the
                 // dependent fma chain of a long sum (the order of the additions changes: ~1e-16 relative)
+                // a factor every term of the entry shares (an operand that does not depend on the summed variables) is
+                // taken out of the sum: (sum of the reduced terms) * factor
+                std::vector<std::string> common;
+                if (factor_common && entry_terms[i].size() >= 2) {
+                    bool all_dyn = true;
+                    for (const Term& t : entry_terms[i]) all_dyn = all_dyn && !t.f.empty();
+                    if (all_dyn) {
+                        common = entry_terms[i][0].f;
+                        for (size_t ti2 = 1; ti2 < entry_terms[i].size() && !common.empty(); ++ti2) {
+                            std::vector<std::string> rest = entry_terms[i][ti2].f, keep;
+                            for (const std::string& f : common) {
+                                auto it = std::find(rest.begin(), rest.end(), f);
+                                if (it != rest.end()) {
+                                    keep.push_back(f);
+                                    rest.erase(it);
+                                }
+                            }
+                            common = keep;
+                        }
+                        for (Term& t : entry_terms[i])
+                            for (const std::string& f : common) t.f.erase(std::find(t.f.begin(), t.f.end(), f));
+                    }
+                }
                 int n_nc = 0;
                 for (const Term& t : entry_terms[i]) n_nc += !t.f.empty();
                 const int na = (n_acc > 1 && n_nc >= 2 * n_acc) ? n_acc : 1;
@@ -620,6 +644,7 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
                     body += "      a += " + lit(konst, f32) + ";\n";
                     ++flops;
                 }
+                for (const std::string& f : common) body += "      a = a * " + f + ";\n", ++flops;
                 if (entry_has_den[i]) {
                     const Term& d = entry_den[i];
                     std::string de;
