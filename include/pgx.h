@@ -116,7 +116,8 @@ typedef struct pgx_plan_desc {
 int pgx_plan_create(const pgx_plan_desc* desc, pgx_plan** out);
 void pgx_plan_destroy(pgx_plan* plan);
 
-/* Bytes of workspace pgx_run_batch needs for a batch of B evidence sets. */
+/* Bytes of workspace pgx_run_batch needs for a batch of B evidence sets with the plan's CURRENT options: 0 once the
+ * plan has been specialised (pgx_plan_specialize) and no other kernel is forced — `workspace` may then be NULL. */
 size_t pgx_workspace_bytes(const pgx_plan* plan, int64_t B);
 
 /* Runs the plan for B evidence sets on `stream` (a cudaStream_t; NULL = default stream).

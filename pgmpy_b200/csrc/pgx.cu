@@ -970,8 +970,14 @@ void pgx_plan_destroy(pgx_plan* plan) {
     delete plan;
 }
 
+// true when pgx_run_batch will launch the plan-specialised kernel (no workspace: its work tables are registers)
+static bool runs_specialized(const pgx_plan* plan) {
+    return plan->spec && plan->n_inputs == 0 && plan->mode != PGX_MODE_STEPWISE && (plan->fused_kernel == 0 || plan->fused_kernel == 4);
+}
+
 size_t pgx_workspace_bytes(const pgx_plan* plan, int64_t B) {
     if (!plan || B <= 0) return 0;
+    if (runs_specialized(plan)) return 0;
     const size_t item = plan->dtype == PGX_F64 ? 8 : 4;
     // head: room for a copy of the batch-invariant tables (32-bit-addressed step kernel); then the work tables
     const size_t head = ((size_t)plan->table_entries + 31) / 32 * 32;
@@ -1569,7 +1575,7 @@ int pgx_run_batch_soft(pgx_plan* plan, const int32_t* ev_states, const void* sof
     if (B <= 0) return fail(PGX_ERR_INVALID, "batch must be positive");
     if (plan->n_ev > 0 && !ev_states) return fail(PGX_ERR_INVALID, "plan has evidence slots but ev_states is null");
     if (!out && plan->out_elems > 0) return fail(PGX_ERR_INVALID, "null output");
-    if (!workspace || workspace_bytes < pgx_workspace_bytes(plan, B))
+    if ((!workspace && pgx_workspace_bytes(plan, B) > 0) || workspace_bytes < pgx_workspace_bytes(plan, B))
         return fail(PGX_ERR_WORKSPACE, "workspace too small: need " + std::to_string(pgx_workspace_bytes(plan, B)) + " bytes");
     cudaStream_t st = (cudaStream_t)stream;
     if (plan->dtype == PGX_F64) return run_typed<double>(plan, ev_states, soft, out, workspace, B, st);

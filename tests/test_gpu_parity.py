@@ -73,6 +73,7 @@ def test_specialized_kernel_vs_oracle(torch_cuda, name, dtype):
     cp = _engine()(plan, dtype=dtype)
     info = cp.specialize()
     assert info["specialized"] and info["registers"] > 0
+    assert cp.workspace_bytes(1000) == 0  # its work tables are registers: no workspace
     want = run_plan(plan.pool, plan.const_blob, states)
     for B in (1, 31, 33, 1000):
         got = cp.run_host(states[:B])
@@ -80,6 +81,7 @@ def test_specialized_kernel_vs_oracle(torch_cuda, name, dtype):
         assert rel_err(got, want[:B]) <= (1e-12 if dtype == "float64" else 1e-5)
     # the table-driven kernel is still there when asked for
     cp.set_mode("fused", 0, "tables-smem")
+    assert cp.workspace_bytes(64) > 0
     got = cp.run_host(states[:64])
     assert cp.last_variant == "tables-smem"
     assert rel_err(got, want[:64]) <= (1e-12 if dtype == "float64" else 1e-5)
