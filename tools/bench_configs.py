@@ -60,6 +60,24 @@ def alarm_ve(batch=1024):
                       "single_variable_queries_per_sec": batch * len(plans) / ms_multi * 1e3,
                       "alg_GBps": multi.plan.algorithmic_bytes(batch) / ms_multi / 1e6,
                       "frac_of_hbm_peak": multi.plan.algorithmic_bytes(batch) / ms_multi / 1e6 / PEAK}), flush=True)
+    # the same plan specialised (one warp per 32 evidence sets runs all 32 pruned queries out of registers)
+    try:
+        ref_out = mout.clone()
+        t0 = time.perf_counter()
+        info = multi.specialize()
+        spec_s = time.perf_counter() - t0
+        ms_spec = timed(lambda: multi.run(ev, out=mout), warm=3, reps=20)
+        assert torch.allclose(mout, ref_out, rtol=1e-12, atol=0)
+        for big in (131072,):
+            _, st_big = sample_evidence(m, big, 5, seed=2, evidence_vars=ev_vars)
+            ev_big = torch.from_numpy(st_big).cuda()
+            out_big = torch.empty((big, multi.out_elems), dtype=torch.float64, device="cuda")
+            ms_big = timed(lambda: multi.run(ev_big, out=out_big), warm=3, reps=20)
+        print(json.dumps({"config": "alarm VE all-variable marginals, ONE plan, specialised kernel", "batch": batch, "variant": multi.last_variant,
+                          "ms_per_batch": ms_spec, "evidence_queries_per_sec": batch / ms_spec * 1e3, "specialize_s": round(spec_s, 2),
+                          "ms_per_131072_sets": ms_big, "evidence_queries_per_sec_at_131072": big / ms_big * 1e3, "spec": info}), flush=True)
+    except Exception as exc:
+        print(json.dumps({"config": "alarm VE all-variable marginals, specialised", "error": str(exc)[:300]}), flush=True)
     ms = timed(run)
     alg = sum(cp.plan.algorithmic_bytes(batch) for cp in plans)
     print(json.dumps({"config": "alarm VE all-variable marginals (one pruned plan per query variable)", "batch": batch,
