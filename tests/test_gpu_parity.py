@@ -567,8 +567,11 @@ def test_discrete_factor_algebra_vectors(torch_cuda):
     assert a == DiscreteFactor(["x2", "x1"], [2, 2], a.values.T)
 
 
-def test_run_pinned_pipeline_matches_device_run(torch_cuda):
-    """End-to-end path (pinned host buffers, chunked over a stream ring) == device-resident path, bit for bit."""
+@pytest.mark.parametrize("specialize", [False, True])
+def test_run_pinned_pipeline_matches_device_run(torch_cuda, specialize):
+    """End-to-end path (pinned host buffers, chunked over a stream ring) == device-resident path, bit for bit — with the
+    table-driven kernel and with the specialised one (persistent CTAs, TMA bulk stores into slices of the ring buffers,
+    ragged last chunk)."""
     torch = torch_cuda
     from pgmpy_b200.inference import BeliefPropagation
 
@@ -576,8 +579,9 @@ def test_run_pinned_pipeline_matches_device_run(torch_cuda):
     bp = BeliefPropagation(m)
     B = 40000  # not a multiple of the chunk size
     ev_vars, states = sample_evidence(m, B, 5, seed=11)
-    cp = bp.marginals_plan(ev_vars)
+    cp = bp.marginals_plan(ev_vars, specialize=specialize)
     want = cp.run(torch.from_numpy(states).cuda()).cpu()
+    assert (cp.last_variant == "specialized") == specialize
     ev_pin = torch.from_numpy(states).pin_memory()
     out_pin = torch.empty((B, cp.out_elems), dtype=torch.float64).pin_memory()
     for chunks in (0, 1, 3, 7):
