@@ -128,6 +128,13 @@ size_t pgx_workspace_bytes(const pgx_plan* plan, int64_t B);
 int pgx_run_batch(pgx_plan* plan, const int32_t* ev_states, void* out, void* workspace, size_t workspace_bytes,
                   int64_t B, void* stream);
 
+/* n independent pgx_run_batch calls enqueued on `stream` by ONE call across the boundary: a mixed-evidence batch
+ * (pgmpy/models/DiscreteBayesianNetwork.py:973-989 feeds the reference one row at a time; here the rows are bucketed
+ * by observed set, one plan per bucket) is a handful of short launches, and the host path of a call per bucket — not
+ * the kernels — was what bounded it. Arrays of n entries; stops at the first error ("job i: ..."). */
+int pgx_run_batch_multi(int32_t n, pgx_plan* const* plans, const int32_t* const* ev_states, void* const* outs,
+                        void* const* workspaces, const size_t* workspace_bytes, const int64_t* B, void* stream);
+
 /* The same for a plan with batch-dependent INPUT tables (soft / virtual evidence, pgmpy/inference/base.py:256-299:
  * one likelihood vector per soft-evidence variable, which the reference adds as an observed binary child per query):
  *   soft       DEVICE dtype [B, in_elems]   row b = the input tables of evidence set b (PGX_INFO_IN_ELEMS, layout in

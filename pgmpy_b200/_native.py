@@ -27,6 +27,7 @@ EXPORTS = (
     "pgx_workspace_bytes",
     "pgx_run_batch",
     "pgx_run_batch_soft",
+    "pgx_run_batch_multi",
     "pgx_plan_set_trace",
     "pgx_run_batch_mpe",
     "pgx_profile_steps",
@@ -85,6 +86,9 @@ def load():
     lib.pgx_workspace_bytes.restype = C.c_size_t
     lib.pgx_run_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p]
     lib.pgx_run_batch.restype = C.c_int
+    lib.pgx_run_batch_multi.argtypes = [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int64), C.c_void_p]
+    lib.pgx_run_batch_multi.restype = C.c_int
     lib.pgx_run_batch_soft.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p]
     lib.pgx_run_batch_soft.restype = C.c_int
     lib.pgx_plan_set_trace.argtypes = [C.c_void_p, i32p, C.c_int64]

@@ -1567,6 +1567,20 @@ int pgx_run_batch(pgx_plan* plan, const int32_t* ev_states, void* out, void* wor
     return pgx_run_batch_soft(plan, ev_states, nullptr, out, workspace, workspace_bytes, B, stream);
 }
 
+int pgx_run_batch_multi(int32_t n, pgx_plan* const* plans, const int32_t* const* ev_states, void* const* outs,
+                        void* const* workspaces, const size_t* workspace_bytes, const int64_t* B, void* stream) {
+    if (n < 0 || (n > 0 && (!plans || !ev_states || !outs || !workspaces || !workspace_bytes || !B)))
+        return fail(PGX_ERR_INVALID, "null argument");
+    for (int32_t i = 0; i < n; ++i) {
+        const int rc = pgx_run_batch(plans[i], ev_states[i], outs[i], workspaces[i], workspace_bytes[i], B[i], stream);
+        if (rc != PGX_OK) {
+            g_err = "job " + std::to_string(i) + ": " + g_err;
+            return rc;
+        }
+    }
+    return PGX_OK;
+}
+
 int pgx_run_batch_soft(pgx_plan* plan, const int32_t* ev_states, const void* soft, void* out, void* workspace,
                        size_t workspace_bytes, int64_t B, void* stream) {
     if (!plan) return fail(PGX_ERR_INVALID, "null plan");

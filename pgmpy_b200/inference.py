@@ -324,13 +324,33 @@ class VariableElimination(_Inference):
         if not jobs:
             return None
         cp0 = jobs[0][0]
-        out = torch.empty((len(evidence_rows), cp0.out_elems), dtype=cp0.torch_dtype, device=cp0.device)
-        # the buckets run one after the other on the current stream. Spreading them over four streams was measured
-        # (tools/bench_configs.py mixed_ve_spec): 16 buckets x 16 384 sets take 0.24 ms in sequence — 15 us of host launch
-        # path per bucket, the kernels themselves are shorter — and 0.40 ms with the fork / join events added
+        # one upload of all evidence, ONE call across the C-ABI for all buckets (pgx_run_batch_multi), one scatter back
+        # into row order: per bucket the host path (~15 us of Python + ctypes, a copy, an indexing kernel) was longer
+        # than the bucket's kernel
+        from .engine import MultiRun
+
+        flat, spans, order = [], [], []
         for cp, states, idx in jobs:
-            res = self._run(cp, states)
-            out[torch.as_tensor(idx, device=res.device)] = res
+            ev = np.ascontiguousarray(np.asarray(states, dtype=np.int32)).reshape(len(idx), cp.n_ev)
+            for j, v in enumerate(cp.plan.ev_vars):
+                if ev.shape[0] and (ev[:, j].min() < 0 or ev[:, j].max() >= self.cardinality[v]):
+                    raise ValueError(f"evidence state index out of range for variable {v}")
+            spans.append((sum(a.size for a in flat), ev.shape))
+            flat.append(ev.ravel())
+            order.extend(idx)
+        with torch.cuda.device(cp0.device):
+            ev_all = torch.from_numpy(np.concatenate(flat) if flat else np.zeros(0, np.int32)).to(cp0.device)
+            res_all = torch.empty((len(order), cp0.out_elems), dtype=cp0.torch_dtype, device=cp0.device)
+            mr_jobs, lo = [], 0
+            for (cp, _, idx), (off, shape) in zip(jobs, spans):
+                ev_t = ev_all[off:off + shape[0] * shape[1]].view(shape) if cp.n_ev else None
+                mr_jobs.append((cp, ev_t, res_all[lo:lo + len(idx)]))
+                lo += len(idx)
+            MultiRun(mr_jobs).run()
+            if order == list(range(len(order))):
+                return res_all
+            out = torch.empty_like(res_all)
+            out[torch.as_tensor(order, device=cp0.device)] = res_all
         return out
 
     # ---- max-product queries ---------------------------------------------

@@ -630,6 +630,35 @@ def test_mixed_evidence_batch_matches_per_row_queries(torch_cuda):
         assert rel_err(out[i], O.ve_query(net, ["HRBP"], row).values) <= 1e-12
 
 
+def test_multi_run_one_call_for_several_plans(torch_cuda):
+    """engine.MultiRun / pgx_run_batch_multi: several plans (specialised and not, different evidence signatures and batch
+    sizes) enqueued by one call across the C-ABI give what the per-plan calls give."""
+    torch = torch_cuda
+    from pgmpy_b200.engine import MultiRun
+
+    m = px.get_example_model("alarm")
+    jt = JTStructure.from_model(m)
+    jobs, want = [], []
+    for i, (k, B) in enumerate([(5, 700), (3, 33), (0, 64), (4, 1)]):
+        ev_vars, states = sample_evidence(m, B, k, seed=40 + i)
+        plan = compile_jt_plan(jt, ev_vars, distribute="ss")
+        cp = _engine()(plan)
+        if i % 2 == 0:
+            cp.specialize()
+        states = states.reshape(B, k) if k else np.zeros((B, 0), np.int32)
+        ev = torch.from_numpy(states).cuda() if k else None
+        out = torch.full((B, cp.out_elems), -1.0, dtype=torch.float64, device="cuda")
+        jobs.append((cp, ev, out))
+        want.append(run_plan(plan.pool, plan.const_blob, states))
+    mr = MultiRun(jobs)
+    for _ in range(2):
+        mr.run()
+    torch.cuda.synchronize()
+    for (cp, ev, out), w in zip(jobs, want):
+        assert rel_err(out.cpu().numpy(), w) <= 1e-12
+    assert jobs[0][0].last_variant == "specialized" and jobs[1][0].last_variant != "specialized"
+
+
 def test_batch_is_tiled_when_the_workspace_would_be_too_large(torch_cuda):
     """Row tiling inside CompiledPlan.run gives the same result as one pass."""
     torch = torch_cuda

@@ -132,8 +132,14 @@ def mixed_ve(name, batch=262144, n_sig=16, specialize=False, n_streams=1):
     compile_s = time.perf_counter() - t0
 
     streams = [torch.cuda.Stream() for _ in range(n_streams)] if n_streams > 1 else []
+    from pgmpy_b200.engine import MultiRun
+
+    multi = MultiRun(jobs) if n_streams == 0 else None  # n_streams = 0: one call across the C-ABI for all buckets
 
     def run():
+        if multi is not None:
+            multi.run()
+            return
         # independent launches of 16 384 evidence sets each: round robin onto a few streams (query_batch_mixed does the same)
         if not streams:
             for cp, ev, o in jobs:
@@ -151,7 +157,7 @@ def mixed_ve(name, batch=262144, n_sig=16, specialize=False, n_streams=1):
     ms = timed(run)
     alg = sum(cp.plan.algorithmic_bytes(per) for cp, _, _ in jobs)
     print(json.dumps({"config": f"{name} VE single-variable posterior, mixed evidence ({n_sig} signatures x {per} sets)", "batch": per * n_sig,
-                      "variant": jobs[0][0].last_variant, "streams": max(1, n_streams),
+                      "variant": jobs[0][0].last_variant, "streams": max(1, n_streams), "one_call_for_all_buckets": n_streams == 0,
                       "plan_compile_s": round(compile_s, 2), "ms_per_batch": ms, "evidence_queries_per_sec": per * n_sig / ms * 1e3,
                       "alg_GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / PEAK}), flush=True)
 
@@ -225,6 +231,10 @@ if __name__ == "__main__":
     if "mixed_ve_spec" in what:
         mixed_ve("hepar2", specialize=True)
         mixed_ve("win95pts", specialize=True)
+        mixed_ve("hepar2", specialize=True, n_streams=0)
+        mixed_ve("win95pts", specialize=True, n_streams=0)
+        mixed_ve("hepar2", specialize=False, n_streams=0)
+        mixed_ve("win95pts", specialize=False, n_streams=0)
     if "mixed_ve_streams" in what:  # measured slower than one stream (host launch bound): kept for the record
         mixed_ve("hepar2", specialize=True, n_streams=4)
         mixed_ve("win95pts", specialize=True, n_streams=4)
