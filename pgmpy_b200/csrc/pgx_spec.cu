@@ -1,17 +1,20 @@
 // pgx_spec.cu — plan-specialised whole-plan kernel: code generator, NVRTC compile, driver-API load and launch.
-// See pgx_spec.h for the idea. The generated kernel computes exactly what k_plan_fused2 computes (same step list,
-// same summation order inside a step); the differences are the ones a compiler can make when every address is known:
+// See pgx_spec.h for the idea and DESIGN.md 4.2 for the measurements behind every choice below. The generated kernel
+// computes what k_plan_fused2 computes (same step list, same summation order inside a step) the way a compiler can
+// when every address and every batch-invariant value is known:
 //
-//   * no offset tables, no index arithmetic: every work-table access is  LDS/STS [lane_base + immediate];
-//   * each DISTINCT operand element of a step is loaded once into a register and reused by all product terms of the
-//     step that need it (the table kernel loads once per term: out x sum x K loads; here: the sum of the operand sizes);
+//   * one warp = one row of 32 evidence sets (lane = evidence set) runs the WHOLE plan; lane l only ever reads what
+//     lane l wrote, so a work-table entry is a local variable (register, or a local-memory spill where ptxas decides):
+//     no offset tables, no index arithmetic, no barrier, no work tables in memory at all;
 //   * batch-invariant operands (CPTs / clique potentials that hold no observed variable) are immediates; the
-//     coefficients of a term are folded on the host and terms with a zero coefficient are not emitted at all
-//     (deterministic CPT rows are common in the bnlearn models);
-//   * one warp runs the whole plan for its 32 evidence sets out of its own shared-memory tables: lane l only ever
-//     reads what lane l wrote, so there is NO barrier until the transposed output stage (__syncwarp);
-//   * work-table entries are packed by lifetime (a message's slots are reused once its last reader has run), which is
-//     what sets the number of resident warps per SM.
+//     coefficients of a term are folded on the host and terms with a zero coefficient are not emitted; entries without
+//     any evidence-dependent factor (messages out of subtrees that hold no evidence) are evaluated here and folded
+//     into their consumers; a CPT entry indexed by one observed variable is a select among immediates;
+//   * only the output entries live in shared memory, laid out as the posterior rows themselves: the kernel is
+//     persistent and every row leaves as ONE TMA bulk store (cp.async.bulk shared -> global) that drains while the
+//     next row computes; the per-variable normalisation takes one branch per row;
+//   * the variants that were measured and lost (several warps per row with level barriers, two warps along a cut of
+//     the junction tree, lock-stepped rows, partial sums, deferred marginals) stay behind PGX_SPEC_* environment knobs.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>

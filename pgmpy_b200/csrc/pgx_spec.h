@@ -2,10 +2,10 @@
 //
 // A junction-tree plan is a fixed list of a few thousand multiply-adds whose operand addresses are all known when the
 // plan is created. pgx_spec_build writes that list out as straight-line CUDA C (one warp = 32 evidence sets, lane =
-// evidence set, work tables in the warp's own shared memory, no barrier anywhere), compiles it for sm_100a with
-// NVRTC and loads it through the driver. Against the table-driven kernel (pgx_fused.cuh) this removes every
-// offset-table load and index addition, loads each operand element once per step instead of once per product term,
-// folds batch-invariant CPT entries into immediates (terms with a zero entry vanish) and needs no level barrier.
+// evidence set, work entries in registers, no barrier anywhere), compiles it for sm_100a with NVRTC and loads it
+// through the driver. Against the table-driven kernel (pgx_fused.cuh) this removes every offset-table load and index
+// addition, keeps every message in a register instead of shared memory, folds batch-invariant CPT entries into
+// immediates (terms with a zero entry vanish) and needs no level barrier; the posterior rows leave by TMA bulk store.
 #pragma once
 #include <cstddef>
 #include <cstdint>
