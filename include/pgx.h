@@ -181,7 +181,8 @@ int pgx_mm_pick(const int32_t* step_record, int32_t item_bytes, int32_t allow_mm
  * the warp's shared memory, batch-invariant CPT entries as immediates), compiles it with NVRTC (dlopen'ed libnvrtc;
  * PGX_ERR_UNSUPPORTED when absent or when the plan has divide / max steps, input tables or more than 120 000 product
  * terms) and loads it; later pgx_run_batch calls use it (PGX_INFO_LAST_VARIANT = 4). The table blob must not change
- * afterwards. Costs seconds: worth it from ~10^8 evidence sets per plan.
+ * afterwards. Costs seconds: worth it from ~10^8 evidence sets per plan. With PGX_SPEC_CACHE_DIR set, compiled kernels
+ * are kept there under the hash of their source and a later process pays a file read instead of the compile.
  * pgx_spec_source: host only, no GPU: the generated source (compile = 0), or compile it too (1; 2 = return the cubin
  * instead of the source). desc->table_blob is a HOST pointer here. Returns the byte count (buf receives at most cap
  * bytes), or < 0 with the reason in buf. stats8 = product terms, terms kept (non-zero coefficient), loads, fp

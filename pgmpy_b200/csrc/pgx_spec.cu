@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -1099,7 +1100,35 @@ Nvrtc& nvrtc() {
 }
 }  // namespace
 
+// Optional on-disk cache of compiled kernels (PGX_SPEC_CACHE_DIR; off when unset): the generated source is a pure
+// function of the plan and the table values, so its 64-bit FNV-1a hash (+ length) names the cubin. A second process
+// serving the same model and evidence signature then pays a file read instead of ~0.5-3 s of NVRTC.
+static std::string cache_path(const std::string& source) {
+    const char* dir = std::getenv("PGX_SPEC_CACHE_DIR");
+    if (!dir || !*dir) return "";
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : source) h = (h ^ c) * 1099511628211ull;
+    char name[96];
+    snprintf(name, sizeof name, "/pgx_spec_sm100a_%016llx_%zu.cubin", (unsigned long long)h, source.size());
+    return std::string(dir) + name;
+}
+
 bool pgx_spec_compile(const std::string& source, std::string& cubin, std::string& log) {
+    const std::string cached = cache_path(source);
+    if (!cached.empty()) {
+        if (FILE* f = fopen(cached.c_str(), "rb")) {
+            fseek(f, 0, SEEK_END);
+            const long sz = ftell(f);
+            fseek(f, 0, SEEK_SET);
+            cubin.resize(sz > 0 ? (size_t)sz : 0);
+            const bool ok = sz > 4 && fread(&cubin[0], 1, (size_t)sz, f) == (size_t)sz && cubin.compare(0, 4, "\x7f" "ELF") == 0;
+            fclose(f);
+            if (ok) {
+                log = "cache hit: " + cached;
+                return true;
+            }
+        }
+    }
     Nvrtc& n = nvrtc();
     if (!n.ok) {
         log = "libnvrtc not found";
@@ -1128,6 +1157,14 @@ bool pgx_spec_compile(const std::string& source, std::string& cubin, std::string
     cubin.resize(cs);
     n.get_cubin(prog, &cubin[0]);
     n.destroy(&prog);
+    if (cs > 0 && !cached.empty()) {
+        const std::string tmp = cached + ".tmp" + std::to_string((long long)getpid());
+        if (FILE* f = fopen(tmp.c_str(), "wb")) {  // write + rename: concurrent ranks never see a partial file
+            const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+            fclose(f);
+            if (!ok || rename(tmp.c_str(), cached.c_str()) != 0) remove(tmp.c_str());
+        }
+    }
     return cs > 0;
 }
 

@@ -69,6 +69,24 @@ def test_generated_source_compiles_for_sm_100a_without_a_gpu():
     assert cubin[:4] == b"\x7fELF" and st["cubin_bytes"] == len(cubin) and st["compile_ms"] > 0
 
 
+def test_compiled_kernels_are_cached_on_disk_when_asked(tmp_path, monkeypatch):
+    """PGX_SPEC_CACHE_DIR: the cubin of a generated source is stored under its hash; the second compile is a file read."""
+    lib = N.load()
+    m = px.get_example_model("child")
+    ev_vars, _ = sample_evidence(m, 1, 4, seed=1)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, distribute="ss")
+    monkeypatch.setenv("PGX_SPEC_CACHE_DIR", str(tmp_path))
+    cubin1, st1 = spec_source(lib, plan, "float64", 2)
+    files = list(tmp_path.glob("pgx_spec_sm100a_*.cubin"))
+    assert len(files) == 1 and files[0].read_bytes() == cubin1
+    cubin2, st2 = spec_source(lib, plan, "float64", 2)
+    assert cubin2 == cubin1 and st2["compile_ms"] <= max(20, st1["compile_ms"] // 5)
+    # a different evidence signature is a different source: its own entry
+    ev2, _ = sample_evidence(m, 1, 3, seed=2)
+    spec_source(lib, compile_jt_plan(JTStructure.from_model(m), ev2, distribute="ss"), "float64", 2)
+    assert len(list(tmp_path.glob("pgx_spec_sm100a_*.cubin"))) == 2
+
+
 def test_plans_the_generator_refuses():
     lib = N.load()
     m = px.get_example_model("alarm")
