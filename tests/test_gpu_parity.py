@@ -124,6 +124,23 @@ def test_marginals_plan_specialize_picks_the_fewest_flops_and_matches(torch_cuda
         assert rel_err(b[:, seg.out_offset:seg.out_offset + n], a[:, o:o + n]) <= 1e-12
 
 
+def test_specialized_kernel_from_the_disk_cache(torch_cuda, tmp_path, monkeypatch):
+    """PGX_SPEC_CACHE_DIR: a second plan object with the same source loads the cached cubin and gives the same posteriors."""
+    monkeypatch.setenv("PGX_SPEC_CACHE_DIR", str(tmp_path))
+    m = px.get_example_model("alarm")
+    ev_vars, states = sample_evidence(m, 200, 5, seed=31)
+    plan = compile_jt_plan(JTStructure.from_model(m), ev_vars, distribute="ss")
+    want = run_plan(plan.pool, plan.const_blob, states)
+    cp1 = _engine()(plan)
+    i1 = cp1.specialize()
+    assert len(list(tmp_path.glob("*.cubin"))) == 1
+    cp2 = _engine()(plan)
+    i2 = cp2.specialize()
+    assert i2["registers"] == i1["registers"] and i2["compile_ms"] < max(50, i1["compile_ms"] // 3)
+    for cp in (cp1, cp2):
+        assert rel_err(cp.run_host(states), want) <= 1e-12 and cp.last_variant == "specialized"
+
+
 def test_specialized_kernel_impossible_evidence_gives_nan(torch_cuda):
     """P(e) = 0: values / values.sum() is NaN in the reference (DiscreteFactor.py:530); so it is here."""
     m = px.get_example_model("asia")
