@@ -274,6 +274,9 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     // output entry. Without this every CTA of a wave computes, then every CTA stores (identical work keeps them in
     // step): measured 33 us of compute + 19 us of stores = 50 us, no overlap.
     bool stage = G == 1 && pack && !(std::getenv("PGX_SPEC_STAGE") && std::atoi(std::getenv("PGX_SPEC_STAGE")) == 0);
+    // measured: 0.0285 ms against 0.0280 with the L1 prefetch at row start (any position 60..100 %): off
+    const bool late_ev = std::getenv("PGX_SPEC_LATE_EV") && std::atoi(std::getenv("PGX_SPEC_LATE_EV")) != 0;  // tuning knobs
+    const int late_ev_pct = std::getenv("PGX_SPEC_LATE_EV_PCT") ? std::max(0, std::min(100, std::atoi(std::getenv("PGX_SPEC_LATE_EV_PCT")))) : 85;
     std::vector<int> out_col0(n_steps, -1);
     const int pitch = out_elems | 1;
     if (stage) {
@@ -476,8 +479,14 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
         for (int c = 0; c <= SWZ; ++c) em.line("  T* const x%d = base2 + (lane ^ %d);", c, c);
     if (stage) {
         em.line("  const long long n_rows = (B + 31) / 32;");
-        // the evidence of the NEXT row is prefetched into L1 while this row computes (a register prefetch was tried: the
-        // five values get spilled at 255 registers and the spill store then waits for the load it was meant to hide)
+        // the evidence of the NEXT row is prefetched into L1 at the start of this row. Loading it into registers at row
+        // start spills (the spill store then waits for the load it was meant to hide); loading it into registers late
+        // in the row (PGX_SPEC_LATE_EV=1) measured no better than the prefetch
+        if (late_ev && n_ev > 0) {
+            em.line("  long long pb = (long long)blockIdx.x * 32 + lane;");
+            em.line("  if (pb >= B) pb = B - 1;");
+            for (int j = 0; j < n_ev; ++j) em.line("  int pe%d = ev[pb * %d + %d];", j, n_ev, j);
+        }
         em.line("  for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {");
         em.line("  const long long row0 = row * 32;");
     } else {
@@ -486,10 +495,13 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
     em.line("  long long b = row0 + lane;");
     em.line("  if (b >= B) b = B - 1;");
     for (int j = 0; j < n_ev; ++j) {
-        em.line("  int e%d = ev[b * %d + %d];", j, n_ev, j);
+        if (stage && late_ev)
+            em.line("  int e%d = pe%d;", j, j);
+        else
+            em.line("  int e%d = ev[b * %d + %d];", j, n_ev, j);
         em.line("  e%d = e%d < 0 ? 0 : (e%d > %d ? %d : e%d);", j, j, j, ev_card[j] - 1, ev_card[j] - 1, j);
     }
-    if (stage && n_ev > 0) {
+    if (stage && n_ev > 0 && !late_ev) {
         em.line("#ifndef PGX_HOST_SIM");
         em.line("  { long long pb = (row + gridDim.x) * 32 + lane; if (pb >= B) pb = B - 1;");
         em.line("    asm volatile(\"prefetch.global.L1 [%%0];\" :: \"l\"(ev + pb * %d)); }", n_ev);
@@ -927,7 +939,17 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
         } else {
             ordered = units;
         }
+        size_t uidx = 0;
+        const size_t ev_at = ordered.size() * (size_t)late_ev_pct / 100;
+        bool ev_loaded = !(stage && late_ev && n_ev > 0);
+        auto load_next_ev = [&]() {
+            em.line("  pb = (row + gridDim.x) * 32 + lane;");
+            em.line("  if (pb >= B) pb = B - 1;");
+            for (int j = 0; j < n_ev; ++j) em.line("  pe%d = ev[pb * %d + %d];", j, n_ev, j);
+            ev_loaded = true;
+        };
         for (const Unit& u : ordered) {
+            if (!ev_loaded && uidx++ >= ev_at) load_next_ev();
             if (skip_compute) break;
             if (!waited && (u.step >= n_steps || in_smem[u.step])) {
                 // the previous row's bulk store reads the staging block: it must have finished before it is rewritten
@@ -940,6 +962,7 @@ bool pgx_spec_generate(const int32_t* pool, int64_t pool_words, const void* host
             em.s += u.code;
             if (R > 1 && ++ui % sync_units == 0) em.line("  __syncthreads();");
         }
+        if (!ev_loaded) load_next_ev();
         em.line("  }");
         phase = 1;
     }
